@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- ALS user+item row-updates/sec at f=64 (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2] [--scale S]
+
+A "step" is one ALS iteration of the hot path (user half + item half, each = Gramian + fused
+per-row Cholesky solve [+ factor all-gather at N > 1]) over the synthetic last.fm-shaped matrix C2
+(360k x 300k, 17M nnz power law, factors=64, Cholesky, lambda=0.01; SURVEY.md section 8(d) generator).
+`value` = (users + items) * K / device time of K iterations with everything resident in HBM;
+`e2e` = the same metric through the public API with HOST inputs: AlternatingLeastSquares.fit(csr) for
+3 iterations from pinned host CSR arrays (H2D), device transpose, and the factors read back (D2H).
+
+One process per GPU (torchrun-compatible env: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT);
+rank 0 prints exactly one JSON line.  --impl reference times the reference's own Cython/OpenMP CPU
+path (oracle/_ref when it was built where /root/reference exists, else the C restatement) on a
+bounded row sample of the same workload, on rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ALS user+item row-updates/sec at f=64"
+UNIT = "row-updates/s"
+E2E_ITERS = 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink rows/cols/nnz together (debugging only)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- helpers
+def algorithmic_bytes_half(nnz, rows, n_other, f):
+    """compulsory bytes of one Cholesky half: index + value + gathered row per nonzero,
+    indptr + written row per solved row; the Gramian read of the other side is its own kernel."""
+    solve = nnz * (4 + 4 + 4 * f) + rows * 4 + rows * 4 * f
+    gram = n_other * 4 * f + 4 * f * f
+    return solve, gram
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_csr(Cui):
+    """Copy of a scipy CSR whose three arrays live in page-locked host memory."""
+    import scipy.sparse as sp
+
+    from implicit_b200 import _lib
+
+    data = _lib.pinned_empty(Cui.data.shape, np.float32)
+    indices = _lib.pinned_empty(Cui.indices.shape, np.int32)
+    indptr = _lib.pinned_empty(Cui.indptr.shape, np.int32)
+    data[:], indices[:], indptr[:] = Cui.data, Cui.indices, Cui.indptr
+    return sp.csr_matrix((data, indices, indptr), shape=Cui.shape, copy=False)
+
+
+# --------------------------------------------------------------------------------------- CPU reference
+def cpu_reference_rate(Cui, X0, Y0, cfg, seconds, kind="auto"):
+    """Times the reference's CPU Cholesky/CG half on a bounded ROW SAMPLE of the workload (all host
+    threads, OPENBLAS_NUM_THREADS=1 as implicit/utils.py:18-62 asks).  Per-row cost depends only on the
+    row's nonzeros, so a uniform row sample scales linearly to the whole iteration."""
+    import oracle
+
+    impl = oracle.get(kind)
+    users, items = Cui.shape
+    Ciu = Cui.T.tocsr()
+    rng = np.random.default_rng(0)
+    solver = (lambda C, X, Y: impl.least_squares_cg(C, X, Y, 0.01, cg_steps=3)) if cfg["use_cg"] else (
+        lambda C, X, Y: impl.least_squares(C, X, Y, 0.01))
+
+    def run(frac):
+        nu, ni = max(64, int(users * frac)), max(64, int(items * frac))
+        su = np.sort(rng.choice(users, min(users, nu), replace=False))
+        si = np.sort(rng.choice(items, min(items, ni), replace=False))
+        Cu, Ci = Cui[su], Ciu[si]
+        Xs, Ys = X0[su].copy(), Y0[si].copy()
+        t = time.perf_counter()
+        solver(Cu, Xs, Y0)
+        solver(Ci, Ys, X0)
+        return len(su) + len(si), time.perf_counter() - t, Cu.nnz + Ci.nnz
+
+    rows, t, _ = run(0.002)  # calibration (also warms the OpenMP pool)
+    frac = min(1.0, max(0.004, 0.002 * seconds / max(t, 1e-3)))
+    rows, t, nnz = run(frac)
+    return {"value": rows / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference" if impl.name == "ref" else "port",
+            "sample": f"uniform {frac:.3%} row sample of both halves ({rows} rows, {nnz} nnz, {t:.1f} s), "
+                      f"{'CG(3)' if cfg['use_cg'] else 'Cholesky'} f={cfg['factors']}, num_threads=0 (all cores)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from implicit_b200 import synthetic
+
+    Cui, X0, Y0, cfg = synthetic.config(args.config, scale=args.scale)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_rate(Cui, X0, Y0, cfg, seconds=1.0)
+    per_step = max(1.0, min(args.cpu_seconds, 150.0 / max(args.steps, 1)))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = cpu_reference_rate(Cui, X0, Y0, cfg, seconds=per_step)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.mean([r["value"] for r in rates]))
+    base = dict(rates[-1], value=value)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * (cfg["users"] + cfg["items"]) / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args, 1), "cpu_baseline": base,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(out))
+
+
+def workload_config(cfg, args, world):
+    return {"workload": f"{args.config}: synthetic power-law CSR {cfg['users']}x{cfg['items']}, {cfg['nnz']} nnz, "
+                        f"factors={cfg['factors']}, {'CG(3)' if cfg['use_cg'] else 'Cholesky'}, lambda=0.01, seed={cfg['seed']}",
+            "scale": args.scale, "l2": "inputs_exceed_l2 (CSR + factors > 126 MB)" if cfg["nnz"] * 8 > 126e6 else "l2_flush",
+            "parallelism": f"row-sharded dp{world}" if world > 1 else "single GPU",
+            "e2e_step": f"fit(host CSR) x {E2E_ITERS} iterations + factors read back"}
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    from implicit_b200 import AlternatingLeastSquares, _lib, synthetic
+    from implicit_b200.distributed import init_process_group
+    from implicit_b200.utils import nnz_balanced_splits
+
+    pg = init_process_group()
+    rank, world, ctx = pg.rank, pg.world, pg.ctx
+    Cui_host, X0, Y0, cfg = synthetic.config(args.config, scale=args.scale)
+    users, items, f = cfg["users"], cfg["items"], cfg["factors"]
+    use_cg = cfg["use_cg"]
+    reg = 0.01
+
+    # ---- device-resident arm
+    Cui = _lib.DeviceCSR.upload(ctx, Cui_host)
+    Ciu = Cui.transpose()
+    X, Y = _lib.DeviceFactors.from_host(ctx, X0), _lib.DeviceFactors.from_host(ctx, Y0)
+    Cui_s, Ciu_s, usplit, isplit = Cui, Ciu, None, None
+    if world > 1:
+        usplit = nnz_balanced_splits(Cui_host.indptr, world)
+        isplit = nnz_balanced_splits(Ciu.indptr_host(), world)
+        Cui_s = Cui.slice_rows(usplit[rank], usplit[rank + 1])
+        Ciu_s = Ciu.slice_rows(isplit[rank], isplit[rank + 1])
+
+    def half(C, A, B, split):
+        if use_cg:
+            _lib.least_squares_cg(ctx, C, A, B, reg, 3)
+        else:
+            _lib.least_squares(ctx, C, A, B, reg)
+        if split is not None:
+            ctx.allgather_rows(A, split)
+
+    def iteration():
+        half(Cui_s, X, Y, usplit)
+        half(Ciu_s, Y, X, isplit)
+
+    flush = cfg["nnz"] * 8 <= 126e6  # small debug scales fit in L2: flush it between iterations
+    for _ in range(max(args.warmup, 3)):
+        iteration()
+    ctx.sync()
+    if world > 1:
+        pg.barrier()
+    sampler = ClockSampler(ctx.device)
+    sampler.start()
+    ctx.profile(True)
+    ctx.profile_read()
+    launches0 = ctx.launch_count()
+    ctx.sync()
+    if world > 1:
+        pg.barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        if flush:
+            ctx.flush_l2()
+        iteration()
+    ms = ctx.timer_stop()
+    ctx.sync()
+    if world > 1:
+        pg.barrier()
+    clocks = sampler.stop()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    launches = ctx.launch_count() - launches0
+    ms_max = pg.allreduce_max(ms) if world > 1 else ms
+    value = (users + items) * args.steps / (ms_max * 1e-3)
+
+    # roofline of the dominant kernel (this rank's shard): algorithmic bytes / measured kernel time
+    ru, _, nu = Cui_s.shape3
+    ri, _, ni = Ciu_s.shape3
+    su, gu = algorithmic_bytes_half(nu, ru, items, f)
+    si, gi = algorithmic_bytes_half(ni, ri, users, f)
+    main_kernel = "cg" if use_cg else "cholesky"
+    aux = "cg_giant" if use_cg else "cholesky_finish"
+    k_ms = prof[main_kernel][0] + prof[aux][0]
+    k_n = prof[main_kernel][1]
+    extra = (ru + ri) * 4 * f if use_cg else 0  # CG also reads the warm start
+    bytes_per_launch = (su + si + extra) / 2.0
+    peak, peak_src = measured_peak_gbs()
+    achieved = (bytes_per_launch * k_n) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": f"{main_kernel}_half_kernel (+ giant-row pass)", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                "traffic": None, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "avg_launch_ms": k_ms / k_n if k_n else None,
+                "kernel_share_of_step": k_ms / ms if ms else None,
+                "gramian_ms_per_launch": prof["gramian"][0] / max(prof["gramian"][1], 1)}
+    whole_iter_bytes = su + si + gu + gi + extra
+    roofline["whole_step_frac"] = whole_iter_bytes * args.steps / (ms * 1e-3) / 1e9 / peak
+
+    # ---- end-to-end arm through the public API with host inputs
+    e2e = None
+    if not args.no_e2e:
+        Cpin = pinned_csr(Cui_host)
+        h2d = Cpin.data.nbytes + Cpin.indices.nbytes + Cpin.indptr.nbytes + X0.nbytes + Y0.nbytes
+        d2h = X0.nbytes + Y0.nbytes
+        reps = max(2, min(5, args.steps))
+        times = []
+        for rep in range(reps + 1):
+            m = AlternatingLeastSquares(factors=f, regularization=reg, use_cg=use_cg, iterations=E2E_ITERS,
+                                        process_group=pg)
+            m.user_factors, m.item_factors = X0, Y0
+            if world > 1:
+                pg.barrier()
+            t = time.perf_counter()
+            m.fit(Cpin, show_progress=False)
+            _ = m.user_factors, m.item_factors  # D2H
+            dt = time.perf_counter() - t
+            if rep > 0:  # first repetition is warm-up
+                times.append(pg.allreduce_max(dt) if world > 1 else dt)
+        e2e = {"value": (users + items) * E2E_ITERS / float(np.mean(times)), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "step": f"fit() of {E2E_ITERS} iterations", "s_per_fit": float(np.mean(times))}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_rate(Cui_host, X0, Y0, cfg, seconds=args.cpu_seconds)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor-core accumulation, fp32-faithful)", "data": "synthetic",
+            "config": workload_config(cfg, args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items() if v[1]},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        pg.barrier()
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: `python bench.py --gpus N` re-launches itself with one process per GPU
+        port = 29500 + os.getpid() % 1000
+        procs = []
+        for r in range(args.gpus):
+            env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(args.gpus), MASTER_ADDR="127.0.0.1",
+                       MASTER_PORT=str(port))
+            procs.append(subprocess.Popen([sys.executable] + sys.argv, env=env))
+        sys.exit(max(p.wait() for p in procs))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,598 @@
+// C-ABI entry points, device containers and the launch schedule (host side of libals_b200.so).
+#include <limits.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.h"
+
+namespace als {
+
+static thread_local char g_err[1024] = {0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  cudaGetLastError();  // clear the sticky-less error state
+  return ALS_E_CUDA;
+}
+
+int ensure_scratch(als_ctx *ctx, int64_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return ALS_OK;
+  if (ctx->scratch) {
+    ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ALS_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+  }
+  int64_t cap = std::max<int64_t>(bytes, 1 << 20);
+  ALS_CUDA(cudaMalloc(&ctx->scratch, cap));
+  ctx->scratch_bytes = cap;
+  return ALS_OK;
+}
+
+int ensure_pinned(als_ctx *ctx, int64_t bytes) {
+  if (bytes <= ctx->pinned_bytes) return ALS_OK;
+  if (ctx->pinned) {
+    ALS_CUDA(cudaStreamSynchronize(ctx->copy));
+    ALS_CUDA(cudaFreeHost(ctx->pinned));
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+  }
+  int64_t cap = std::max<int64_t>(bytes, 1 << 20);
+  ALS_CUDA(cudaMallocHost(&ctx->pinned, cap));
+  ctx->pinned_bytes = cap;
+  return ALS_OK;
+}
+
+// Longest-first schedule.  Rows with more than kSplitNnz nonzeros are cut into chunks of kChunkNnz
+// so that one power-law giant (139k nnz in C2) cannot serialise the tail.
+int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr) {
+  std::vector<WorkItem> items;
+  std::vector<WorkItem> fin;
+  items.reserve((size_t)csr->rows + 64);
+  int64_t slots = 0;
+  for (int64_t r = 0; r < csr->rows; ++r) {
+    const int32_t b = indptr[r], e = indptr[r + 1];
+    const int32_t n = e - b;
+    if (n > kSplitNnz) {
+      const int32_t nchunks = (int32_t)ceil_div(n, kChunkNnz);
+      fin.push_back(WorkItem{(int32_t)r, (int32_t)slots, nchunks, -2});
+      for (int32_t c = 0; c < nchunks; ++c) {
+        const int32_t k0 = b + c * kChunkNnz;
+        const int32_t k1 = std::min(e, k0 + kChunkNnz);
+        items.push_back(WorkItem{(int32_t)r, k0, k1, (int32_t)slots});
+        ++slots;
+      }
+    } else {
+      items.push_back(WorkItem{(int32_t)r, b, e, -1});
+    }
+  }
+  // counting sort, descending by length (lengths <= kSplitNnz)
+  {
+    std::vector<int64_t> count(kSplitNnz + 2, 0);
+    for (const WorkItem &w : items) ++count[kSplitNnz - (w.k1 - w.k0)];
+    int64_t acc = 0;
+    for (size_t i = 0; i < count.size(); ++i) {
+      int64_t c = count[i];
+      count[i] = acc;
+      acc += c;
+    }
+    std::vector<WorkItem> sorted(items.size());
+    for (const WorkItem &w : items) sorted[count[kSplitNnz - (w.k1 - w.k0)]++] = w;
+    items.swap(sorted);
+  }
+  csr->n_work = (int64_t)items.size();
+  csr->n_finish = (int64_t)fin.size();
+  csr->n_slots = slots;
+  if (csr->n_work) {
+    ALS_CUDA(cudaMalloc(&csr->work, sizeof(WorkItem) * items.size()));
+    ALS_CUDA(cudaMemcpyAsync(csr->work, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice,
+                             ctx->stream));
+  }
+  if (csr->n_finish) {
+    ALS_CUDA(cudaMalloc(&csr->finish, sizeof(WorkItem) * fin.size()));
+    ALS_CUDA(cudaMemcpyAsync(csr->finish, fin.data(), sizeof(WorkItem) * fin.size(), cudaMemcpyHostToDevice,
+                             ctx->stream));
+  }
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vectors die here
+  return ALS_OK;
+}
+
+ProfScope::ProfScope(als_ctx *c, int w) : ctx(c), which(w) {
+  if (!ctx->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) {
+    cudaEventRecord(e, ctx->stream);
+    ctx->prof_events[which].push_back(e);
+  }
+}
+ProfScope::~ProfScope() {
+  if (!ctx->profiling || (ctx->prof_events[which].size() & 1) == 0) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) {
+    cudaEventRecord(e, ctx->stream);
+    ctx->prof_events[which].push_back(e);
+  } else {
+    cudaEventDestroy(ctx->prof_events[which].back());
+    ctx->prof_events[which].pop_back();
+  }
+}
+
+__global__ void scale_kernel(float *data, int64_t n, float alpha) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) data[i] *= alpha;
+}
+
+__global__ void fill_kernel(float *data, int64_t n, float v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) data[i] = v;
+}
+
+}  // namespace als
+
+using namespace als;
+
+// ---- context -----------------------------------------------------------------------------------
+ALS_API int als_abi_version(void) { return ALS_B200_ABI_VERSION; }
+ALS_API const char *als_last_error(void) { return g_err; }
+
+ALS_API int als_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+ALS_API int als_ctx_create(int device, als_ctx **out) {
+  ALS_REQUIRE(out != nullptr, "als_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  ALS_CUDA(cudaGetDeviceCount(&n));
+  ALS_REQUIRE(device >= 0 && device < n, "als_ctx_create: device %d out of range (%d visible)", device, n);
+  ALS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ALS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("als_ctx_create: device %d is sm_%d%d; libals_b200 is built for sm_100a only", device, prop.major,
+              prop.minor);
+    return ALS_E_UNSUPPORTED;
+  }
+  als_ctx *ctx = new als_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->l2_bytes = prop.l2CacheSize;
+  ctx->mem_bytes = (int64_t)prop.totalGlobalMem;
+  strncpy(ctx->name, prop.name, sizeof(ctx->name) - 1);
+  ALS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ALS_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+  ALS_CUDA(cudaEventCreate(&ctx->ev0));
+  ALS_CUDA(cudaEventCreate(&ctx->ev1));
+  ALS_CUDA(cudaMalloc(&ctx->G, sizeof(float) * 256 * 256));
+  ALS_CUDA(cudaMalloc(&ctx->Greg, sizeof(float) * 256 * 256));
+  ALS_CUDA(cudaMalloc(&ctx->counters, sizeof(int32_t) * 16));
+  ALS_CUDA(cudaMalloc(&ctx->bad_row, sizeof(long long) * 2));
+  ALS_CUDA(cudaMalloc(&ctx->dscalars, sizeof(double) * 8));
+  *out = ctx;
+  return ALS_OK;
+}
+
+ALS_API int als_ctx_destroy(als_ctx *ctx) {
+  if (!ctx) return ALS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy);
+  als_comm_destroy(ctx);
+  cudaFree(ctx->G);
+  cudaFree(ctx->Greg);
+  cudaFree(ctx->gram_partials);
+  cudaFree(ctx->counters);
+  cudaFree(ctx->bad_row);
+  cudaFree(ctx->dscalars);
+  cudaFree(ctx->scratch);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy);
+  delete ctx;
+  return ALS_OK;
+}
+
+ALS_API int als_sync(als_ctx *ctx) {
+  ALS_REQUIRE(ctx, "als_sync: ctx is NULL");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->copy));
+  return ALS_OK;
+}
+
+ALS_API int als_device_info(als_ctx *ctx, char *name, int *sm_count, int64_t *l2_bytes, int64_t *mem_bytes) {
+  ALS_REQUIRE(ctx, "als_device_info: ctx is NULL");
+  if (name) strncpy(name, ctx->name, 256);
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (l2_bytes) *l2_bytes = ctx->l2_bytes;
+  if (mem_bytes) *mem_bytes = ctx->mem_bytes;
+  return ALS_OK;
+}
+
+ALS_API int64_t als_launch_count(als_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+ALS_API int als_timer_start(als_ctx *ctx) {
+  ALS_REQUIRE(ctx, "als_timer_start: ctx is NULL");
+  ALS_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  return ALS_OK;
+}
+
+ALS_API int als_timer_stop(als_ctx *ctx, float *ms) {
+  ALS_REQUIRE(ctx && ms, "als_timer_stop: NULL argument");
+  ALS_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  ALS_CUDA(cudaEventSynchronize(ctx->ev1));
+  ALS_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return ALS_OK;
+}
+
+ALS_API int als_flush_l2(als_ctx *ctx, int64_t bytes) {
+  ALS_REQUIRE(ctx && bytes > 0, "als_flush_l2: bad argument");
+  static float *flush = nullptr;  // separate from scratch: scratch holds live solver state
+  static int64_t flush_bytes = 0;
+  if (bytes > flush_bytes) {
+    if (flush) ALS_CUDA(cudaFree(flush));
+    ALS_CUDA(cudaMalloc(&flush, bytes));
+    flush_bytes = bytes;
+  }
+  fill_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(flush, bytes / 4, 1.0f);
+  ALS_CUDA(cudaGetLastError());
+  return ALS_OK;
+}
+
+ALS_API int als_profile_enable(als_ctx *ctx, int on) {
+  ALS_REQUIRE(ctx, "als_profile_enable: ctx is NULL");
+  ctx->profiling = on != 0;
+  return ALS_OK;
+}
+
+ALS_API int als_profile_read(als_ctx *ctx, int which, double *ms_total, int64_t *launches) {
+  ALS_REQUIRE(ctx && which >= 0 && which < 8 && ms_total && launches, "als_profile_read: bad argument");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<cudaEvent_t> &ev = ctx->prof_events[which];
+  double total = 0.0;
+  int64_t n = 0;
+  for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) {
+      total += ms;
+      ++n;
+    }
+  }
+  for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  ev.clear();
+  *ms_total = total;
+  *launches = n;
+  return ALS_OK;
+}
+
+ALS_API int als_host_alloc(void **ptr, int64_t bytes) {
+  ALS_REQUIRE(ptr && bytes >= 0, "als_host_alloc: bad argument");
+  ALS_CUDA(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+  return ALS_OK;
+}
+
+ALS_API int als_host_free(void *ptr) {
+  if (ptr) ALS_CUDA(cudaFreeHost(ptr));
+  return ALS_OK;
+}
+
+// ---- CSR ---------------------------------------------------------------------------------------
+ALS_API int als_csr_upload(als_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz, const int32_t *indptr,
+                           const int32_t *indices, const float *data, int64_t row_offset, als_csr **out) {
+  ALS_REQUIRE(ctx && out && indptr, "als_csr_upload: NULL argument");
+  ALS_REQUIRE(rows >= 0 && cols >= 0 && nnz >= 0, "als_csr_upload: negative shape");
+  ALS_REQUIRE(nnz < (int64_t)INT32_MAX && rows < (int64_t)INT32_MAX && cols < (int64_t)INT32_MAX,
+              "als_csr_upload: int32 CSR only (rows, cols, nnz < 2^31), like implicit/gpu/matrix.h:93-100");
+  ALS_REQUIRE(indptr[0] >= 0 && (int64_t)indptr[rows] - indptr[0] == nnz,
+              "als_csr_upload: indptr[rows] - indptr[0] = %lld != nnz = %lld",
+              (long long)indptr[rows] - indptr[0], (long long)nnz);
+  ALS_REQUIRE(nnz == 0 || (indices && data), "als_csr_upload: indices/data NULL with nnz > 0");
+  *out = nullptr;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  als_csr *c = new als_csr();
+  c->ctx = ctx;
+  c->rows = rows;
+  c->cols = cols;
+  c->nnz = nnz;
+  c->row_offset = row_offset;
+  // a row shard arrives with indptr[0] != 0: rebase
+  std::vector<int32_t> rebased;
+  const int32_t base = indptr[0];
+  const int32_t *ip = indptr;
+  if (base != 0) {
+    rebased.resize(rows + 1);
+    for (int64_t r = 0; r <= rows; ++r) rebased[r] = indptr[r] - base;
+    ip = rebased.data();
+  }
+  for (int64_t r = 0; r < rows; ++r) {
+    if (ip[r + 1] < ip[r]) {
+      delete c;
+      set_error("als_csr_upload: indptr is not monotone at row %lld", (long long)r);
+      return ALS_E_INVALID;
+    }
+  }
+  ALS_CUDA(cudaMalloc(&c->indptr, sizeof(int32_t) * (rows + 1)));
+  ALS_CUDA(cudaMalloc(&c->indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+  ALS_CUDA(cudaMalloc(&c->data, sizeof(float) * std::max<int64_t>(nnz, 1)));
+  ALS_CUDA(cudaMemcpyAsync(c->indptr, ip, sizeof(int32_t) * (rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz) {
+    ALS_CUDA(cudaMemcpyAsync(c->indices, indices + base, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    ALS_CUDA(cudaMemcpyAsync(c->data, data + base, sizeof(float) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int rc = build_schedule(ctx, c, ip);
+  if (rc != ALS_OK) {
+    als_csr_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return ALS_OK;
+}
+
+ALS_API int als_csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out) {
+  ALS_REQUIRE(ctx && in && out, "als_csr_transpose: NULL argument");
+  return als::csr_transpose(ctx, in, out);
+}
+
+ALS_API int als_csr_slice_rows(als_ctx *ctx, const als_csr *in, int64_t r0, int64_t r1, als_csr **out) {
+  ALS_REQUIRE(ctx && in && out, "als_csr_slice_rows: NULL argument");
+  ALS_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= in->rows, "als_csr_slice_rows: bad row range [%lld, %lld)", (long long)r0,
+              (long long)r1);
+  ALS_REQUIRE(in->row_offset == 0, "als_csr_slice_rows: cannot slice a shard");
+  *out = nullptr;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t rows = r1 - r0;
+  std::vector<int32_t> ip((size_t)rows + 1);
+  ALS_CUDA(cudaMemcpyAsync(ip.data(), in->indptr + r0, sizeof(int32_t) * (rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  als_csr *c = new als_csr();
+  c->ctx = ctx;
+  c->rows = rows;
+  c->cols = in->cols;
+  c->nnz = (int64_t)ip[rows] - ip[0];
+  c->row_offset = r0;
+  c->owns = false;
+  c->indptr = in->indptr + r0;  // absolute positions into the parent's indices/data
+  c->indices = in->indices;
+  c->data = in->data;
+  int rc = build_schedule(ctx, c, ip.data());
+  if (rc != ALS_OK) {
+    als_csr_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return ALS_OK;
+}
+
+ALS_API int als_csr_scale(als_ctx *ctx, als_csr *csr, float alpha) {
+  ALS_REQUIRE(ctx && csr, "als_csr_scale: NULL argument");
+  if (csr->nnz == 0) return ALS_OK;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  scale_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(csr->data, csr->nnz, alpha);
+  ALS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return ALS_OK;
+}
+
+ALS_API int als_csr_shape(const als_csr *csr, int64_t *rows, int64_t *cols, int64_t *nnz) {
+  ALS_REQUIRE(csr, "als_csr_shape: NULL");
+  if (rows) *rows = csr->rows;
+  if (cols) *cols = csr->cols;
+  if (nnz) *nnz = csr->nnz;
+  return ALS_OK;
+}
+
+ALS_API int als_csr_download(als_ctx *ctx, const als_csr *csr, int32_t *indptr, int32_t *indices, float *data) {
+  ALS_REQUIRE(ctx && csr, "als_csr_download: NULL argument");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (indptr) ALS_CUDA(cudaMemcpy(indptr, csr->indptr, sizeof(int32_t) * (csr->rows + 1), cudaMemcpyDeviceToHost));
+  if (indices && csr->nnz)
+    ALS_CUDA(cudaMemcpy(indices, csr->indices, sizeof(int32_t) * csr->nnz, cudaMemcpyDeviceToHost));
+  if (data && csr->nnz) ALS_CUDA(cudaMemcpy(data, csr->data, sizeof(float) * csr->nnz, cudaMemcpyDeviceToHost));
+  return ALS_OK;
+}
+
+ALS_API int als_csr_destroy(als_csr *csr) {
+  if (!csr) return ALS_OK;
+  if (csr->ctx) {
+    cudaSetDevice(csr->ctx->device);
+    cudaStreamSynchronize(csr->ctx->stream);
+  }
+  if (csr->owns) {
+    cudaFree(csr->indptr);
+    cudaFree(csr->indices);
+    cudaFree(csr->data);
+  }
+  cudaFree(csr->work);
+  cudaFree(csr->finish);
+  delete csr;
+  return ALS_OK;
+}
+
+// ---- factors -----------------------------------------------------------------------------------
+ALS_API int als_factors_create(als_ctx *ctx, int64_t rows, int factors, als_factors **out) {
+  ALS_REQUIRE(ctx && out, "als_factors_create: NULL argument");
+  ALS_REQUIRE(rows >= 0 && factors > 0, "als_factors_create: bad shape (%lld, %d)", (long long)rows, factors);
+  ALS_REQUIRE(factors <= 256, "als_factors_create: factors=%d > 256 is not supported", factors);
+  *out = nullptr;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  als_factors *f = new als_factors();
+  f->ctx = ctx;
+  f->rows = rows;
+  f->f = factors;
+  f->ld = round_up(factors, 16);
+  const int64_t bytes = sizeof(float) * std::max<int64_t>(rows, 1) * f->ld;
+  ALS_CUDA(cudaMalloc(&f->d, bytes));
+  ALS_CUDA(cudaMemsetAsync(f->d, 0, bytes, ctx->stream));
+  *out = f;
+  return ALS_OK;
+}
+
+ALS_API int als_factors_upload(als_ctx *ctx, als_factors *f, const float *host, int64_t row0, int64_t nrows) {
+  ALS_REQUIRE(ctx && f && host, "als_factors_upload: NULL argument");
+  ALS_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= f->rows, "als_factors_upload: rows [%lld, %lld) out of range",
+              (long long)row0, (long long)(row0 + nrows));
+  if (nrows == 0) return ALS_OK;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  // ordered after any kernel already queued on the compute stream that reads/writes f
+  ALS_CUDA(cudaMemcpy2DAsync(f->d + row0 * f->ld, sizeof(float) * f->ld, host, sizeof(float) * f->f,
+                             sizeof(float) * f->f, nrows, cudaMemcpyHostToDevice, ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffer may be pageable and reused by the caller
+  return ALS_OK;
+}
+
+ALS_API int als_factors_download(als_ctx *ctx, const als_factors *f, float *host, int64_t row0, int64_t nrows) {
+  ALS_REQUIRE(ctx && f && host, "als_factors_download: NULL argument");
+  ALS_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= f->rows,
+              "als_factors_download: rows [%lld, %lld) out of range", (long long)row0, (long long)(row0 + nrows));
+  if (nrows == 0) return ALS_OK;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  ALS_CUDA(cudaMemcpy2DAsync(host, sizeof(float) * f->f, f->d + row0 * f->ld, sizeof(float) * f->ld,
+                             sizeof(float) * f->f, nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ALS_OK;
+}
+
+ALS_API int als_factors_shape(const als_factors *f, int64_t *rows, int *factors, int *stride) {
+  ALS_REQUIRE(f, "als_factors_shape: NULL");
+  if (rows) *rows = f->rows;
+  if (factors) *factors = f->f;
+  if (stride) *stride = f->ld;
+  return ALS_OK;
+}
+
+ALS_API int als_factors_destroy(als_factors *f) {
+  if (!f) return ALS_OK;
+  if (f->ctx) {
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+  }
+  cudaFree(f->d);
+  delete f;
+  return ALS_OK;
+}
+
+// ---- hot path ----------------------------------------------------------------------------------
+static int check_half(const char *who, als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y) {
+  ALS_REQUIRE(ctx && C && X && Y, "%s: NULL argument", who);
+  ALS_REQUIRE(C->ctx == ctx && X->ctx == ctx && Y->ctx == ctx, "%s: objects belong to different contexts", who);
+  ALS_REQUIRE(X->f == Y->f, "%s: X has %d factors, Y has %d", who, X->f, Y->f);
+  ALS_REQUIRE(C->cols == Y->rows, "%s: C has %lld columns but Y has %lld rows", who, (long long)C->cols,
+              (long long)Y->rows);
+  ALS_REQUIRE(C->row_offset + C->rows <= X->rows, "%s: C rows [%lld, %lld) exceed X's %lld rows", who,
+              (long long)C->row_offset, (long long)(C->row_offset + C->rows), (long long)X->rows);
+  return ALS_OK;
+}
+
+ALS_API int als_gramian(als_ctx *ctx, const als_factors *Y, float *G_host) {
+  ALS_REQUIRE(ctx && Y, "als_gramian: NULL argument");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  int rc = launch_gramian(ctx, Y);
+  if (rc != ALS_OK) return rc;
+  if (G_host) {
+    std::vector<float> tmp((size_t)Y->ld * Y->ld);
+    ALS_CUDA(cudaMemcpyAsync(tmp.data(), ctx->G, sizeof(float) * tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < Y->f; ++i) memcpy(G_host + (size_t)i * Y->f, tmp.data() + (size_t)i * Y->ld, sizeof(float) * Y->f);
+  }
+  return ALS_OK;
+}
+
+static int finish_cholesky(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, double reg,
+                           int64_t *bad_row) {
+  int rc = launch_regularize(ctx, Y->f, Y->ld, (float)reg);
+  if (rc != ALS_OK) return rc;
+  rc = launch_cholesky(ctx, C, X, Y);
+  if (rc != ALS_OK) return rc;
+  long long bad = -1;
+  ALS_CUDA(cudaMemcpyAsync(&bad, ctx->bad_row, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (bad_row) *bad_row = (bad == LLONG_MAX) ? -1 : (int64_t)bad;
+  if (bad != LLONG_MAX) {
+    set_error("cholesky failed on row %lld: normal equations not positive definite. Try increasing the "
+              "regularization parameter.", bad);
+    return ALS_E_NOT_POSDEF;
+  }
+  return ALS_OK;
+}
+
+ALS_API int als_least_squares(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
+                              double regularization, int64_t *bad_row) {
+  int rc = check_half("als_least_squares", ctx, C, X, Y);
+  if (rc != ALS_OK) return rc;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  rc = launch_gramian(ctx, Y);
+  if (rc != ALS_OK) return rc;
+  return finish_cholesky(ctx, C, X, Y, regularization, bad_row);
+}
+
+ALS_API int als_least_squares_with_gramian(als_ctx *ctx, const float *YtY_host, const als_csr *C, als_factors *X,
+                                           const als_factors *Y, double regularization, int64_t *bad_row) {
+  int rc = check_half("als_least_squares_with_gramian", ctx, C, X, Y);
+  if (rc != ALS_OK) return rc;
+  ALS_REQUIRE(YtY_host, "als_least_squares_with_gramian: YtY is NULL");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  std::vector<float> tmp((size_t)Y->ld * Y->ld, 0.f);
+  for (int i = 0; i < Y->f; ++i) memcpy(tmp.data() + (size_t)i * Y->ld, YtY_host + (size_t)i * Y->f, sizeof(float) * Y->f);
+  ALS_CUDA(cudaMemcpyAsync(ctx->G, tmp.data(), sizeof(float) * tmp.size(), cudaMemcpyHostToDevice, ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return finish_cholesky(ctx, C, X, Y, regularization, bad_row);
+}
+
+ALS_API int als_least_squares_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
+                                 float regularization, int cg_steps) {
+  int rc = check_half("als_least_squares_cg", ctx, C, X, Y);
+  if (rc != ALS_OK) return rc;
+  ALS_REQUIRE(cg_steps >= 0, "als_least_squares_cg: cg_steps < 0");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  rc = launch_gramian(ctx, Y);
+  if (rc != ALS_OK) return rc;
+  rc = launch_regularize(ctx, Y->f, Y->ld, regularization);
+  if (rc != ALS_OK) return rc;
+  return launch_cg(ctx, C, X, Y, cg_steps);
+}
+
+ALS_API int als_calculate_loss(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y,
+                               float regularization, double *loss) {
+  ALS_REQUIRE(loss, "als_calculate_loss: loss is NULL");
+  int rc = check_half("als_calculate_loss", ctx, C, const_cast<als_factors *>(X), Y);
+  if (rc != ALS_OK) return rc;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  rc = launch_gramian(ctx, Y);
+  if (rc != ALS_OK) return rc;
+  return launch_loss(ctx, C, X, Y, regularization, loss);
+}
+
+ALS_API int als_topk(als_ctx *ctx, const als_factors *items, const als_factors *queries, const int32_t *query_rows,
+                     int64_t n_query, int k, const float *item_norms_host, const als_csr *liked,
+                     const int32_t *filter_items, int64_t n_filter, int32_t *ids_host, float *scores_host) {
+  ALS_REQUIRE(ctx && items && queries && ids_host && scores_host, "als_topk: NULL argument");
+  ALS_REQUIRE(items->f == queries->f, "als_topk: items have %d factors, queries %d", items->f, queries->f);
+  ALS_REQUIRE(k >= 0 && n_query >= 0, "als_topk: negative k or n_query");
+  ALS_REQUIRE(!liked || liked->rows == n_query, "als_topk: liked has %lld rows for %lld queries",
+              liked ? (long long)liked->rows : 0LL, (long long)n_query);
+  ALS_REQUIRE(!liked || liked->cols == items->rows, "als_topk: liked has %lld columns for %lld items",
+              liked ? (long long)liked->cols : 0LL, (long long)items->rows);
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  return launch_topk(ctx, items, queries, query_rows, n_query, k, item_norms_host, liked, filter_items, n_filter,
+                     ids_host, scores_host);
+}

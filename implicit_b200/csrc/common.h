@@ -1,0 +1,136 @@
+// Internal declarations shared by the translation units of libals_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/als_b200.h"
+
+#define ALS_API extern "C" __attribute__((visibility("default")))
+
+namespace als {
+
+// ---- error plumbing (no exceptions cross the C boundary) ------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define ALS_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess) return ::als::cuda_fail(e__, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define ALS_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::als::set_error(__VA_ARGS__);      \
+      return ALS_E_INVALID;               \
+    }                                     \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- work schedule ------------------------------------------------------------------------------
+// One unit of work for the per-row solvers.  kind: 0 = whole row (k0..k1 = its nnz range),
+// 1 = a chunk of a giant row (partial normal equations go to `slot`), 2 = finish a giant row
+// (k0 = first slot, k1 = number of slots).
+struct WorkItem {
+  int32_t row;
+  int32_t k0;
+  int32_t k1;
+  int32_t slot;  // -1: whole row; >= 0: chunk slot; -2: finish item
+};
+
+constexpr int kSplitNnz = 3072;   // rows longer than this are split ...
+constexpr int kChunkNnz = 2048;   // ... into chunks of this many nonzeros (multiple of 8)
+
+}  // namespace als
+
+struct als_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int64_t l2_bytes = 0;
+  int64_t mem_bytes = 0;
+  char name[256] = {0};
+  cudaStream_t stream = nullptr;   // compute
+  cudaStream_t copy = nullptr;     // H2D / D2H staging
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  // Gramian state: G (f_pad x f_pad, without lambda) and Greg (G + lambda I, identity on padded dims)
+  float *G = nullptr;
+  float *Greg = nullptr;
+  float *gram_partials = nullptr;
+  int64_t gram_partials_cap = 0;
+  // per-launch scalars: [0] work counter, [1] second counter, [2..3] bad row (int64)
+  int32_t *counters = nullptr;
+  long long *bad_row = nullptr;
+  double *dscalars = nullptr;  // loss accumulators (8 doubles)
+  // generic scratch (giant-row partial slots, L2 flush, top-k staging)
+  void *scratch = nullptr;
+  int64_t scratch_bytes = 0;
+  // pinned host staging
+  void *pinned = nullptr;
+  int64_t pinned_bytes = 0;
+  // per-kernel profiling (als_profile_*)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events[8];  // pairs (start, stop) per category
+  // NCCL
+  void *comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+struct als_factors {
+  als_ctx *ctx = nullptr;
+  int64_t rows = 0;
+  int f = 0;   // logical factors
+  int ld = 0;  // device row stride (multiple of 16, zero padded)
+  float *d = nullptr;
+};
+
+struct als_csr {
+  als_ctx *ctx = nullptr;
+  int64_t rows = 0, cols = 0, nnz = 0, row_offset = 0;
+  int32_t *indptr = nullptr;
+  int32_t *indices = nullptr;
+  float *data = nullptr;
+  bool owns = true;  // false for a row-slice view sharing its parent's arrays
+  // schedule
+  als::WorkItem *work = nullptr;    // main pass: whole rows + chunks, longest first
+  int64_t n_work = 0;
+  als::WorkItem *finish = nullptr;  // finish pass: one per giant row
+  int64_t n_finish = 0;
+  int64_t n_slots = 0;
+};
+
+namespace als {
+
+// RAII bracket: records start/stop events around a kernel launch when profiling is on.
+struct ProfScope {
+  als_ctx *ctx;
+  int which;
+  ProfScope(als_ctx *c, int w);
+  ~ProfScope();
+};
+enum { kProfGramian = 0, kProfCholesky = 1, kProfCholFinish = 2, kProfCg = 3, kProfCgGiant = 4, kProfTopk = 5, kProfLoss = 6 };
+
+int ensure_scratch(als_ctx *ctx, int64_t bytes);
+int ensure_pinned(als_ctx *ctx, int64_t bytes);
+int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr_host);
+int csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out);
+
+// kernels' host launchers (each returns an ALS_* code)
+int launch_gramian(als_ctx *ctx, const als_factors *Y);                  // -> ctx->G
+int launch_regularize(als_ctx *ctx, int f, int ld, float lambda);         // ctx->G -> ctx->Greg
+int launch_cholesky(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y);
+int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps);
+int launch_loss(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y, float reg,
+                double *loss);
+int launch_topk(als_ctx *ctx, const als_factors *items, const als_factors *queries, const int32_t *query_rows,
+                int64_t n_query, int k, const float *item_norms_host, const als_csr *liked,
+                const int32_t *filter_items, int64_t n_filter, int32_t *ids_host, float *scores_host);
+
+}  // namespace als

@@ -34,10 +34,19 @@
 static inline void s_axpy(int n, float a, const float *x, float *y) {
   for (int i = 0; i < n; ++i) y[i] += a * x[i];
 }
+/* sdot: OpenBLAS's x86 kernels keep 32 interleaved fp32 partial sums (4 AVX2 accumulators of 8 lanes)
+ * and add them pairwise at the end; a single running sum would be measurably LESS accurate than the
+ * reference on all-positive data (the first ALS half-iteration), so the restatement mirrors that. */
 static inline float s_dot(int n, const float *x, const float *y) {
-  float s = 0.f;
-  for (int i = 0; i < n; ++i) s += x[i] * y[i];
-  return s;
+  float acc[32];
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  int i = 0;
+  for (; i + 32 <= n; i += 32)
+    for (int j = 0; j < 32; ++j) acc[j] += x[i + j] * y[i + j];
+  for (int j = 0; i < n; ++i, ++j) acc[j] += x[i] * y[i];
+  for (int w = 16; w >= 1; w >>= 1)
+    for (int j = 0; j < w; ++j) acc[j] += acc[j + w];
+  return acc[0];
 }
 /* y = alpha * A x with A symmetric (ssymv 'U', beta = 0); A is stored full so rows are used. */
 static inline void s_symv(int n, float alpha, const float *A, const float *x, float *y) {

@@ -1,0 +1,53 @@
+"""CPU-only: the C-ABI library builds/loads, exports every symbol include/als_b200.h declares, and the
+ctypes table covers exactly that set.  No compute calls (there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "als_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(als_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from implicit_b200 import _build
+
+    path = _build.build()
+    lib = ctypes.CDLL(path)
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/als_b200.h but not exported"
+    assert lib.als_abi_version() == 1
+
+
+def test_ctypes_table_matches_header():
+    from implicit_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_no_gpu_means_loud_failure():
+    """There is no CPU fallback: without a device, creating a context raises."""
+    from implicit_b200 import _lib
+
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(_lib.AlsError):
+        _lib.Context(0)
+
+
+def test_product_does_not_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under implicit_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "implicit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f

@@ -1,0 +1,259 @@
+"""Black-box API tests against implicit_b200.AlternatingLeastSquares, following the reference's own
+RecommenderBaseTestMixin (tests/recommender_base_test.py) and tests/als_test.py for the ALS rows."""
+import io
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+from scipy.sparse import coo_matrix, csr_matrix, random as sprandom
+
+pytestmark = pytest.mark.gpu
+
+
+def get_checker_board(X):
+    """tests/recommender_base_test.py:20-28"""
+    ret = np.zeros((X, X))
+    for i in range(X):
+        for j in range(i % 2, X, 2):
+            ret[i, j] = 1.0
+    return csr_matrix(ret - np.eye(X))
+
+
+def _get_model(**kw):
+    from implicit_b200 import AlternatingLeastSquares
+
+    args = dict(factors=32, regularization=0, random_state=23)  # tests/als_test.py:17-19
+    args.update(kw)
+    return AlternatingLeastSquares(**args)
+
+
+@pytest.fixture(scope="module", params=[True, False], ids=["cg", "cholesky"])
+def fitted(request):
+    item_users = get_checker_board(50)
+    user_items = item_users.T.tocsr()
+    model = _get_model(use_cg=request.param)
+    model.fit(item_users, show_progress=False)
+    return model, user_items
+
+
+def test_recommend(fitted):
+    """recommender_base_test.py:38-63"""
+    model, user_items = fitted
+    for userid in range(50):
+        ids, _ = model.recommend(userid, user_items[userid], N=1)
+        assert len(ids) == 1
+        assert ids[0] == userid
+    ids, _ = model.recommend(0, user_items[0], N=10000)
+    assert len(ids)
+    ids, _ = model.recommend(0, user_items[0], N=1, filter_items=[0])
+    assert 0 not in set(ids)
+    with pytest.raises(ValueError):
+        model.recommend(0, user_items[0], items=[1, 2], filter_items=[0])
+
+
+def test_recommend_batch(fitted):
+    """recommender_base_test.py:65-109: batch == scalar"""
+    model, user_items = fitted
+    userids = np.arange(50)
+    ids, scores = model.recommend(userids, user_items[userids], N=1)
+    for userid in range(50):
+        assert ids[userid][0] == userid
+    ids, scores = model.recommend(userids, user_items[userids], N=10, filter_items=[0, 2, 4])
+    for userid in userids:
+        i1, s1 = model.recommend(userid, user_items[userid], N=10, filter_items=[0, 2, 4])
+        np.testing.assert_array_equal(ids[userid], i1)
+        np.testing.assert_allclose(scores[userid], s1, rtol=1e-6)
+    items = np.arange(0, 50, 3)
+    ids, scores = model.recommend(userids, user_items[userids], N=5, items=items)
+    assert set(ids.ravel().tolist()) <= set(items.tolist())
+    for userid in (0, 7, 33):
+        i1, s1 = model.recommend(userid, user_items[userid], N=5, items=items)
+        np.testing.assert_array_equal(ids[userid], i1)
+
+
+def test_fit_ordering(fitted):
+    """recommender_base_test.py:317-335: scores non-increasing"""
+    model, user_items = fitted
+    _, scores = model.recommend(np.arange(50), user_items, N=20, filter_already_liked_items=False)
+    assert np.all(np.diff(scores, axis=1) <= 0)
+
+
+def test_recalculate_user(fitted):
+    """recommender_base_test.py:111-145: recalculated == stored"""
+    model, user_items = fitted
+    model.regularization = 0.01 if model.use_cg else model.regularization
+    for userid in (0, 1, 17):
+        ids, scores = model.recommend(userid, user_items[userid], N=5, recalculate_user=False)
+        rids, rscores = model.recommend(userid, user_items[userid], N=5, recalculate_user=True)
+        assert ids[0] == rids[0] == userid
+    batch = np.array([3, 4, 5])
+    f = model.recalculate_user(batch, user_items[batch])
+    assert f.shape == (3, 32)
+    for j, u in enumerate(batch):
+        np.testing.assert_allclose(f[j], model.recalculate_user(int(u), user_items[int(u)]), rtol=1e-4, atol=1e-5)
+
+
+def test_rank_items_errors(fitted):
+    """recommender_base_test.py:346-389"""
+    model, user_items = fitted
+    with pytest.raises(IndexError):
+        model.recommend(0, user_items[0], items=[0, 1, 2, 50])
+    with pytest.raises(IndexError):
+        model.recommend(0, user_items[0], items=[-1, 1])
+    with pytest.raises(ValueError):
+        model.recommend(0, user_items[:2])
+    with pytest.raises(ValueError):
+        model.recommend(0, user_items[0].tocoo())
+
+
+def test_similar_items(fitted):
+    """recommender_base_test.py:161-283 (ALS-relevant part)"""
+    model, _ = fitted
+    for itemid in range(50):
+        ids, scores = model.similar_items(itemid, N=10)
+        assert ids[0] == itemid
+        assert scores[0] == pytest.approx(1.0, abs=1e-4)
+        for r in ids:
+            assert r % 2 == itemid % 2
+    ids, _ = model.similar_items(0, N=5, filter_items=[0, 2])
+    assert 0 not in ids and 2 not in ids
+    ids, _ = model.similar_items(0, N=5, items=np.arange(0, 50, 2))
+    assert set(ids.tolist()) <= set(range(0, 50, 2))
+    bids, bscores = model.similar_items(np.arange(50), N=10)
+    for itemid in (0, 13, 49):
+        ids, scores = model.similar_items(itemid, N=10)
+        np.testing.assert_array_equal(bids[itemid], ids)
+    ids, _ = model.similar_users(3, N=4)
+    assert ids[0] == 3
+
+
+def test_zero_length_row():
+    """recommender_base_test.py:285-302"""
+    item_users = get_checker_board(50).tolil()
+    item_users[42, :] = 0
+    item_users = item_users.tocsr()
+    user_items = item_users.T.tocsr()
+    model = _get_model()
+    model.fit(item_users, show_progress=False)
+    for itemid in range(40):
+        ids, _ = model.similar_items(itemid, N=10)
+        assert 42 not in ids
+    ids, _ = model.recommend(0, user_items[0], N=5)
+    assert len(ids) == 5
+
+
+def test_fit_non_csr_matrix():
+    """recommender_base_test.py:304-315"""
+    from implicit_b200 import ParameterWarning
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        _get_model(iterations=1).fit(get_checker_board(20).tocoo(), show_progress=False)
+    assert any(issubclass(x.category, ParameterWarning) for x in w)
+
+
+def test_dtype_and_callback():
+    """recommender_base_test.py:337-344, :472-487"""
+    calls = []
+    model = _get_model(iterations=3)
+    model.fit(get_checker_board(30).astype(np.float64), show_progress=False,
+              callback=lambda it, t, loss: calls.append((it, t, loss)))
+    assert [c[0] for c in calls] == [0, 1, 2]
+    assert model.user_factors.dtype == np.float32
+
+
+@pytest.mark.parametrize("use_cg", [True, False])
+def test_factorize(use_cg):
+    """tests/als_test.py:142-186"""
+    counts = csr_matrix(
+        [[1, 1, 0, 1, 0, 0], [0, 1, 1, 1, 0, 0], [1, 0, 1, 0, 0, 0], [1, 1, 0, 0, 0, 0], [0, 0, 1, 1, 0, 1],
+         [0, 1, 0, 0, 0, 1], [0, 0, 0, 0, 1, 1]], dtype=np.float64)
+    model = _get_model(factors=6, regularization=0, alpha=2.0, use_cg=use_cg, random_state=42)
+    model.fit(counts, show_progress=False)
+    rec = model.user_factors.dot(model.item_factors.T)
+    dense = counts.toarray()
+    for r in range(7):
+        for c in range(6):
+            assert dense[r, c] == pytest.approx(rec[r, c], abs=1e-3), (r, c, rec)
+
+
+def test_cg_nan():
+    """tests/als_test.py:74-139: degenerate inputs must not produce NaN/inf"""
+    raw = [[0.0, 2.0, 1.5, 1.33333333, 1.25, 1.2, 0, 0, 0, 0, 0, 0],
+           [0.0, 0.0, 2.0, 1.5, 1.33333333, 1.25, 0, 0, 0, 0, 0, 0],
+           [0.0, 0.0, 0.0, 2.0, 1.5, 1.33333333, 0, 0, 0, 0, 0, 0],
+           [0.0, 0.0, 0.0, 0.0, 2.0, 1.5, 0, 0, 0, 0, 0, 0]]
+    counts = csr_matrix(raw, dtype=np.float64)
+    model = _get_model(factors=3, regularization=0.01, use_cg=True)
+    model.fit(counts, show_progress=False)
+    assert np.isfinite(model.user_factors).all() and np.isfinite(model.item_factors).all()
+    Ciu = sprandom(100, 100, density=0.0005, format="coo", dtype=np.float32, random_state=42).T.tocsr()
+    model = _get_model(factors=32, regularization=10, iterations=10, use_cg=True, random_state=23)
+    model.fit(Ciu, show_progress=False)
+    assert np.isfinite(model.user_factors).all() and np.isfinite(model.item_factors).all()
+
+
+def test_small_nan():
+    """tests/als_test.py:255-269: factors > users"""
+    model = _get_model(factors=100, regularization=0.01, use_cg=False)
+    model.fit(csr_matrix(np.ones((5, 7), dtype=np.float32)), show_progress=False)
+    assert np.isfinite(model.user_factors).all()
+
+
+def test_zero_iterations_with_loss():
+    """tests/als_test.py:37-42"""
+    model = _get_model(factors=128, iterations=0, calculate_training_loss=True)
+    model.fit(csr_matrix(np.ones((10, 10))), show_progress=False)
+
+
+def test_incremental_retrain():
+    """tests/als_test.py:272-301"""
+    likes = get_checker_board(50)
+    model = _get_model(factors=2, regularization=0, use_cg=False)
+    model.fit(likes, show_progress=False)
+    ids, _ = model.recommend(0, likes[0])
+    assert ids[0] == 0
+    likes = coo_matrix(([1.0, 1.0, 1.0], ([0, 0, 0], [1, 100, 101])), shape=(1, 102)).tocsr()  # new items
+    model.partial_fit_users([50], csr_matrix(([1.0, 1.0], ([0, 0], [0, 2])), shape=(1, 50)))
+    assert model.user_factors.shape[0] == 51
+    ids, _ = model.recommend(50, csr_matrix(([1.0, 1.0], ([0, 0], [0, 2])), shape=(1, 50)), N=3)
+    assert all(i % 2 == 0 for i in ids)
+    model.partial_fit_items([50, 51], csr_matrix(([1.0, 1.0], ([0, 1], [0, 1])), shape=(2, 51)))
+    assert model.item_factors.shape[0] == 52
+    assert likes.shape == (1, 102)
+
+
+def test_pickle_and_save_load(fitted):
+    """recommender_base_test.py:408-470"""
+    from implicit_b200 import AlternatingLeastSquares
+
+    model, user_items = fitted
+    ids, scores = model.recommend(np.arange(10), user_items[:10], N=5)
+    clone = pickle.loads(pickle.dumps(model))
+    ids2, scores2 = clone.recommend(np.arange(10), user_items[:10], N=5)
+    np.testing.assert_array_equal(ids, ids2)
+    buf = io.BytesIO()
+    model.save(buf)
+    buf.seek(0)
+    loaded = AlternatingLeastSquares.load(buf)
+    ids3, _ = loaded.recommend(np.arange(10), user_items[:10], N=5)
+    np.testing.assert_array_equal(ids, ids3)
+    assert loaded.factors == model.factors and loaded.cg_steps == 3
+
+
+def test_cholesky_failure_raises_value_error():
+    model = _get_model(factors=8, regularization=0, use_cg=False, iterations=1)
+    model.user_factors = np.zeros((2, 8), dtype=np.float32)
+    model.item_factors = np.zeros((3, 8), dtype=np.float32)
+    with pytest.raises(ValueError):
+        model.fit(csr_matrix(np.array([[1, 0, 0], [0, 1, 1]], dtype=np.float32)), show_progress=False)
+
+
+def test_no_cpu_path():
+    from implicit_b200 import AlternatingLeastSquares
+
+    with pytest.raises(ValueError):
+        AlternatingLeastSquares(use_gpu=False)
+    with pytest.raises(ValueError):
+        AlternatingLeastSquares(dtype=np.float64)
