@@ -497,4 +497,6 @@ def _filter_items_from_sparse_matrix(items, query_items):
     coo.data[items[positions] != coo.col] = 0
     coo.col = positions
     coo.eliminate_zeros()
-    return coo.tocsr()
+    out = coo.tocsr()
+    # the reference keeps the original column count; positions index the subset, so shrink to it
+    return csr_matrix((out.data, out.indices, out.indptr), shape=(out.shape[0], len(items)))

@@ -105,16 +105,19 @@ __device__ __forceinline__ float4 nnz_pass(const Team<F, TW> &tm, const int32_t 
   const int gid = tm.warp * C::NG + tm.grp;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   constexpr int UN = 4;
-  int k = k0 + gid;
-  for (; k + (UN - 1) * TG < k1; k += UN * TG) {
+  // The trip count must be uniform across the warp (the group reductions are full-warp shuffles):
+  // every group walks the same kb and masks its own out-of-range nonzeros to y = 0.
+  for (int kb = k0; kb < k1; kb += UN * TG) {
     float4 y[UN];
     float c[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const int idx = __ldg(indices + k + u * TG);
-      c[u] = __ldg(data + k + u * TG);
-      y[u] = tm.active ? __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx * F) + tm.sub)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = kb + u * TG + gid;
+      const bool valid = k < k1;
+      const int idx = valid ? __ldg(indices + k) : 0;
+      c[u] = valid ? __ldg(data + k) : 0.f;
+      y[u] = (tm.active && valid) ? __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx * F) + tm.sub)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -122,19 +125,8 @@ __device__ __forceinline__ float4 nnz_pass(const Team<F, TW> &tm, const int32_t 
       const float conf = fabsf(c[u]);
       const float pos = (FIRST && c[u] > 0.f) ? c[u] : 0.f;
       const float coef = pos - sign * (conf - 1.f) * d;
-      axpy4(acc, coef, y[u]);
+      axpy4(acc, coef, y[u]);  // masked nonzeros have y == 0
     }
-  }
-  for (; k < k1; k += TG) {
-    const int idx = __ldg(indices + k);
-    const float cc = __ldg(data + k);
-    const float4 y = tm.active ? __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx * F) + tm.sub)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float d = group_sum<C::L>(dot4(y, v));
-    const float conf = fabsf(cc);
-    const float pos = (FIRST && cc > 0.f) ? cc : 0.f;
-    const float coef = pos - sign * (conf - 1.f) * d;
-    axpy4(acc, coef, y);
   }
   return acc;
 }
@@ -254,15 +246,17 @@ loss_nnz_kernel(const int32_t *__restrict__ indices, const float *__restrict__ d
     if (w.w == -2) continue;
     const float4 x = active ? __ldg(reinterpret_cast<const float4 *>(X + (row_offset + w.x) * F) + sub)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = w.y + grp; k < w.z; k += C::NG) {
-      const int idx = __ldg(indices + k);
-      const float c = __ldg(data + k);
-      const float4 y = active ? __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx * F) + sub)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kb = w.y; kb < w.z; kb += C::NG) {  // uniform trip count: full-warp shuffles inside
+      const int k = kb + grp;
+      const bool valid = k < w.z;
+      const int idx = valid ? __ldg(indices + k) : 0;
+      const float c = valid ? __ldg(data + k) : 0.f;
+      const float4 y = (active && valid) ? __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx * F) + sub)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
       const float d = group_sum<C::L>(dot4(y, x));
       const float conf = fabsf(c);
       const float temp = (c > 0.f ? -2.f * c : 0.f) + (conf - 1.f) * d;
-      if (sub == 0) {
+      if (sub == 0 && valid) {
         term += (double)(temp * d) + (double)conf;
         conf_sum += (double)conf;
       }

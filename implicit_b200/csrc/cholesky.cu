@@ -44,11 +44,14 @@ __device__ __forceinline__ void cp_async_wait() {
 constexpr uint32_t kTf32Mask = 0xffffe000u;  // keep sign, exponent and the 10 TF32 mantissa bits
 constexpr uint32_t kSignBit = 0x80000000u;
 
-// hi = x truncated to TF32 (exactly representable), lo = x - hi (exact in fp32; the tensor core
-// ignores its low 13 bits, an O(2^-22 |x|) effect)
+// hi = x rounded to nearest TF32 (add half an ulp of the 10-bit mantissa, then clear the low 13 bits),
+// lo = (x - hi) -- exact in fp32 -- rounded the same way.  Rounding (instead of letting the tensor core
+// truncate) halves the error of each term and, more importantly, removes its bias: on all-positive
+// data (the first ALS half-iteration) truncation errors add up linearly instead of as a random walk.
+__device__ __forceinline__ uint32_t rn_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & kTf32Mask; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
-  hi = __float_as_uint(x) & kTf32Mask;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - __uint_as_float(hi));
 }
 
 template <int NB>
@@ -479,9 +482,7 @@ int launch_cholesky(als_ctx *ctx, const als_csr *C, als_factors *X, const als_fa
     case 3: return run_cholesky<3>(ctx, C, X, Y);
     case 4: return run_cholesky<4>(ctx, C, X, Y);
     default:
-      set_error("cholesky: factors=%d (padded %d) > 64 is not supported yet by the register-resident solver", Y->f,
-                Y->ld);
-      return ALS_E_UNSUPPORTED;
+      return launch_cholesky_wide(ctx, C, X, Y);  // 64 < padded factors <= 128: cholesky_wide.cu
   }
 }
 

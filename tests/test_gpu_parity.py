@@ -365,9 +365,26 @@ def test_c2_full_size_sampled_rows_match_oracle(lib, ctx, orc):
                                        np.where(lens == 0)[0][:2]]))
     got = _gpu_half(lib, ctx, Cui, X0, Y0, 0.01, use_cg=False)
     sub = Cui[sample]
+    # (1) solver parity on IDENTICAL inputs: the reference's _least_squares (implicit/cpu/_als.pyx:76) is given
+    #     the Gramian the GPU computed, so only the per-row accumulate + Cholesky differ.
+    dY = lib.DeviceFactors.from_host(ctx, Y0)
+    G_gpu = lib.gramian(ctx, dY)
+    dY.close()
+    exp_same = np.zeros((len(sample), 64), dtype=np.float32)
+    orc._least_squares(G_gpu, sub.indptr, sub.indices, sub.data.astype("float32"), exp_same, Y0, 0.01)
+    e_same = row_err(got[sample], exp_same)
+    # (2) the reference end to end: its own np.dot(Y.T, Y) is an fp32 sgemm over 300k all-positive rows whose
+    #     rounding noise (reported below against fp64) is amplified by the cold-start conditioning.
     exp = np.zeros((len(sample), 64), dtype=np.float32)
     orc.least_squares(sub, exp, Y0, 0.01)
     e = row_err(got[sample], exp)
-    print(f"C2 sampled rows: max {e.max():.2e} median {np.median(e):.2e}; longest row {lens.max()}")
-    assert e.max() < CHOL_MAX
+    G64 = Y0.astype(np.float64).T @ Y0.astype(np.float64)
+    g_gpu = np.abs(G_gpu - G64).max() / np.abs(G64).max()
+    g_ref = np.abs(np.dot(Y0.T, Y0) - G64).max() / np.abs(G64).max()
+    print(f"C2 sampled rows, same Gramian: max {e_same.max():.2e} median {np.median(e_same):.2e}; "
+          f"reference end to end: max {e.max():.2e} median {np.median(e):.2e}; "
+          f"Gramian rel err vs fp64: gpu {g_gpu:.1e} reference sgemm {g_ref:.1e}; longest row {lens.max()}")
+    assert e_same.max() < CHOL_MAX
+    assert e.max() < 1e-3 and np.median(e) < 1e-4
+    assert g_gpu < 1e-6
     assert not np.isnan(got).any()
