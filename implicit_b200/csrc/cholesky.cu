@@ -3,7 +3,8 @@
 // One warp owns one row u of the CSR at a time (persistent warps pull rows, longest first, from an
 // atomic work counter):
 //   gather   the factor rows Y[i] of the row's nonzeros are staged 8 at a time into shared memory
-//            with 16-byte cp.async copies (3-deep ring per warp, prefetched across row boundaries);
+//            with 16-byte cp.async copies (3-deep ring per warp, prefetched across row boundaries;
+//            indices / confidences are prefetched 32 at a time into registers one block ahead);
 //   A, b     A_u = (Y^T Y + lambda I) + sum_k (|c_k| - 1) y_k y_k^T is accumulated in REGISTERS as the
 //            upper-triangular set of 16x8 mma.sync.m16n8k8 TF32 tiles, with the 3xTF32 split
 //            (hi*hi + hi*lo + lo*hi) so the result is fp32-faithful (plain TF32 would miss the 1e-4
@@ -49,9 +50,12 @@ constexpr uint32_t kSignBit = 0x80000000u;
 // truncate) halves the error of each term and, more importantly, removes its bias: on all-positive
 // data (the first ALS half-iteration) truncation errors add up linearly instead of as a random walk.
 __device__ __forceinline__ uint32_t rn_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & kTf32Mask; }
+// lo is handed over raw: the tensor core drops its low 13 bits, an error of at most 2^-21 |x| that is
+// unbiased because, with hi rounded to nearest, lo is symmetric around zero.  (Rounding lo as well
+// cost two more integer ops per value -- 17% of the kernel's instructions -- for no measurable gain.)
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
   hi = rn_tf32(x);
-  lo = rn_tf32(x - __uint_as_float(hi));
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 template <int NB>
@@ -61,7 +65,7 @@ struct Cfg {
   static constexpr int NTILES = NB * (NB + 1);
   static constexpr int LDS = F + 8;         // staged-row stride: conflict-free fragment reads
   static constexpr int NSTAGE = 3;
-  static constexpr int STAGE_FLOATS = 8 * LDS + 16;  // 8 rows + w[8] + cpos[8]
+  static constexpr int STAGE_FLOATS = 8 * LDS + 16;  // 8 rows + sw[8] + cpos[8]
   // packed U: panel p holds rows 8p..8p+7, columns 8p..F-1; stride == 8 or 24 (mod 32)
   __host__ __device__ static constexpr int pstride(int p) { return F - 8 * p + ((p & 1) ? 0 : 8); }
   __host__ __device__ static constexpr int poff(int p) {
@@ -70,7 +74,7 @@ struct Cfg {
     return o;
   }
   static constexpr int U_FLOATS = poff(NT8);
-  static constexpr int WARP_FLOATS = NSTAGE * STAGE_FLOATS + U_FLOATS + F /* z */;
+  static constexpr int WARP_FLOATS = NSTAGE * STAGE_FLOATS + U_FLOATS + F /* z */ + F /* 1/pivot */;
   // index of tile (i, j), j >= 2i, in the upper-triangular tile list
   __host__ __device__ static constexpr int tidx(int i, int j) { return i * NT8 - i * (i - 1) + (j - 2 * i); }
   static constexpr int SLOT_FLOATS = 32 * (NTILES * 4 + NT8);
@@ -84,28 +88,46 @@ struct RowState {
   float bp[Cfg<NB>::NT8];  // b partials: b[8c + g] = sum over the 4 lanes of group g of bp[c]
 };
 
-// ---- gather ------------------------------------------------------------------------------------
+// 32 consecutive nonzeros of a row, one per lane, prefetched into registers well before the k-steps
+// that gather them (the index load would otherwise sit on the critical path of every k-step).
+struct Blk {
+  int idx;   // column index, -1 past the end of the row
+  float c;   // raw confidence; decoded only when the k-step is issued, so the load stays in flight
+};
+
+__device__ __forceinline__ Blk load_block(const WorkItem &wi, int b, const int32_t *__restrict__ indices,
+                                          const float *__restrict__ data, int lane) {
+  const int k = wi.k0 + 32 * b + lane;
+  const bool valid = k < wi.k1;
+  Blk r;
+  r.idx = valid ? __ldg(indices + k) : -1;
+  r.c = valid ? __ldg(data + k) : 0.f;
+  return r;
+}
+
+// ---- gather: k-step s (0..3) of block `blk` -> stage -----------------------------------------------
 template <int NB>
-__device__ __forceinline__ void issue_kstep(float *stage, const WorkItem &wi, int ks, const int32_t *__restrict__ indices,
-                                            const float *__restrict__ data, const float *__restrict__ Y, int lane) {
+__device__ __forceinline__ void issue_kstep(float *stage, const Blk &blk, int s, bool active,
+                                            const float *__restrict__ Y, int lane) {
   using C = Cfg<NB>;
-  const int kbase = wi.k0 + 8 * ks;
-  if (kbase < wi.k1) {
-    const int k = kbase + (lane & 7);
-    const bool valid = k < wi.k1;
-    const int idx = __ldg(indices + (valid ? k : wi.k0));
-    const float c = valid ? __ldg(data + k) : 0.f;
+  if (active) {  // warp uniform
+    const int src = 8 * s + (lane & 7);
+    const float c = __shfl_sync(0xffffffffu, blk.c, src);
+    const int myidx = __shfl_sync(0xffffffffu, blk.idx, src);
     if (lane < 8) {
-      // confidence > 0: b += c y, A += (c - 1) y y^T;  else: A += (-c - 1) y y^T   (_als.pyx:115-124)
-      stage[8 * C::LDS + lane] = valid ? (fabsf(c) - 1.f) : 0.f;
-      stage[8 * C::LDS + 8 + lane] = c > 0.f ? c : 0.f;
+      // A += w y y^T with w = |c| - 1 = sign(w) (sqrt|w| y)(sqrt|w| y)^T; b += c y for c > 0   (_als.pyx:115-124)
+      const float w = (myidx >= 0) ? fabsf(c) - 1.f : 0.f;
+      stage[8 * C::LDS + lane] = copysignf(__fsqrt_rn(fabsf(w)), w);
+      stage[8 * C::LDS + 8 + lane] = (myidx >= 0 && c > 0.f) ? c : 0.f;
     }
+    const int first = __shfl_sync(0xffffffffu, blk.idx, 8 * s);  // the first row of an active k-step exists
     constexpr int CH = C::F / 4;  // 16-byte chunks per factor row
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
       const int id = q * 32 + lane;
       const int row = id / CH, ch = id % CH;
-      const int ridx = __shfl_sync(0xffffffffu, idx, row);
+      int ridx = __shfl_sync(0xffffffffu, blk.idx, 8 * s + row);
+      if (ridx < 0) ridx = first;  // padding rows carry sw = cp = 0
       cp_async16(stage + row * C::LDS + ch * 4, Y + (int64_t)ridx * C::F + ch * 4);
     }
   }
@@ -116,57 +138,63 @@ __device__ __forceinline__ void issue_kstep(float *stage, const WorkItem &wi, in
 template <int NB>
 __device__ __forceinline__ void consume_kstep(RowState<NB> &st, const float *stage, int g, int t) {
   using C = Cfg<NB>;
-  const float w0 = stage[8 * C::LDS + t], w1 = stage[8 * C::LDS + t + 4];
+  const float s0 = stage[8 * C::LDS + t], s1 = stage[8 * C::LDS + t + 4];
   const float c0 = stage[8 * C::LDS + 8 + t], c1 = stage[8 * C::LDS + 8 + t + 4];
-  uint32_t yh0[C::NT8], yl0[C::NT8], yh1[C::NT8], yl1[C::NT8];
-  float y0[C::NT8], y1[C::NT8];
+  const float a0 = fabsf(s0), a1 = fabsf(s1);
+  const uint32_t m0 = __float_as_uint(s0) & kSignBit, m1 = __float_as_uint(s1) & kSignBit;
+  uint32_t vh0[C::NT8], vl0[C::NT8], vh1[C::NT8], vl1[C::NT8];
 #pragma unroll
   for (int c = 0; c < C::NT8; ++c) {
-    y0[c] = stage[t * C::LDS + 8 * c + g];
-    y1[c] = stage[(t + 4) * C::LDS + 8 * c + g];
+    const float y0 = stage[t * C::LDS + 8 * c + g];
+    const float y1 = stage[(t + 4) * C::LDS + 8 * c + g];
+    st.bp[c] = fmaf(c0, y0, st.bp[c]);
+    st.bp[c] = fmaf(c1, y1, st.bp[c]);
+    split_tf32(a0 * y0, vh0[c], vl0[c]);  // v = sqrt|w| y: one split serves both mma operands
+    split_tf32(a1 * y1, vh1[c], vl1[c]);
   }
+  // Term-major order: the three 3xTF32 terms of one tile chain through its accumulator, so they are
+  // issued a full sweep of tiles apart instead of back to back (an HMMA result takes ~35 cycles).
 #pragma unroll
-  for (int c = 0; c < C::NT8; ++c) {
-    st.bp[c] = fmaf(c0, y0[c], st.bp[c]);
-    st.bp[c] = fmaf(c1, y1[c], st.bp[c]);
-    split_tf32(y0[c], yh0[c], yl0[c]);
-    split_tf32(y1[c], yh1[c], yl1[c]);
-  }
+  for (int term = 0; term < 3; ++term) {
 #pragma unroll
-  for (int i = 0; i < NB; ++i) {
-    // A fragment rows: z = w * y for factor indices 16i + g (a0,a2) and 16i + 8 + g (a1,a3)
-    uint32_t ah[4], al[4];
-    split_tf32(w0 * y0[2 * i], ah[0], al[0]);
-    split_tf32(w0 * y0[2 * i + 1], ah[1], al[1]);
-    split_tf32(w1 * y1[2 * i], ah[2], al[2]);
-    split_tf32(w1 * y1[2 * i + 1], ah[3], al[3]);
+    for (int i = 0; i < NB; ++i) {
+      // A fragment: rows 16i + g (a0, a2) and 16i + 8 + g (a1, a3) of sign(w) v; lo part for term 0
+      const uint32_t a0 = (term == 0 ? vl0[2 * i] : vh0[2 * i]) ^ m0;
+      const uint32_t a1 = (term == 0 ? vl0[2 * i + 1] : vh0[2 * i + 1]) ^ m0;
+      const uint32_t a2 = (term == 0 ? vl1[2 * i] : vh1[2 * i]) ^ m1;
+      const uint32_t a3 = (term == 0 ? vl1[2 * i + 1] : vh1[2 * i + 1]) ^ m1;
 #pragma unroll
-    for (int j = 2 * i; j < C::NT8; ++j) {
-      float(&d)[4] = st.acc[C::tidx(i, j)];
-      mma_tf32(d, al[0], al[1], al[2], al[3], yh0[j], yh1[j]);
-      mma_tf32(d, ah[0], ah[1], ah[2], ah[3], yl0[j], yl1[j]);
-      mma_tf32(d, ah[0], ah[1], ah[2], ah[3], yh0[j], yh1[j]);
+      for (int j = 2 * i; j < C::NT8; ++j) {
+        float(&d)[4] = st.acc[C::tidx(i, j)];
+        if (term == 1) mma_tf32(d, a0, a1, a2, a3, vl0[j], vl1[j]);  // hi * lo
+        else mma_tf32(d, a0, a1, a2, a3, vh0[j], vh1[j]);            // lo * hi, then hi * hi
+      }
     }
   }
 }
 
 // ---- blocked Cholesky + solves -----------------------------------------------------------------
-// Returns false when a pivot is not positive (LAPACK posv info != 0, _als.pyx:131-138).
+// Right-looking, 8-row panels.  Panel p is spilled from the accumulator tiles to shared memory; one
+// lane owns one panel column (plus the rhs slice as an extra column) and the 8 pivots are eliminated
+// in order: the pivot lane broadcasts 1/sqrt(d), every lane scales its row-r entry, the lanes of the
+// diagonal block broadcast U[r][r'] and every lane updates its later rows.  The trailing matrix is
+// then updated in registers with 3xTF32 mma tiles.  A non-positive pivot yields a non-finite
+// solution, which is how failure is detected (LAPACK posv info != 0, _als.pyx:131-138).
 template <int NB>
-__device__ __forceinline__ bool factor_solve(RowState<NB> &st, float *U, float *zb, float *__restrict__ xout, int lane) {
+__device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *zb, float *dinv,
+                                             float *__restrict__ xout, int lane, bool &ok) {
   using C = Cfg<NB>;
   constexpr int F = C::F;
   const int g = lane >> 2, t = lane & 3;
-  bool ok = true;
 
 #pragma unroll
   for (int p = 0; p < C::NT8; ++p) {
     const int i = p >> 1, h = p & 1;
     float *Up = U + C::poff(p);
-    constexpr int dummy = 0;
-    (void)dummy;
     const int sp = C::pstride(p);
     const int Wp = F - 8 * p;
+    constexpr int NJmax = (F + 1 + 31) / 32;
+    const int NJ = (Wp + 1 + 31) / 32;
     // 1. spill panel rows 8p..8p+7 (columns 8p..F-1) and the matching slice of b
 #pragma unroll
     for (int j = p; j < C::NT8; ++j) {
@@ -180,51 +208,50 @@ __device__ __forceinline__ bool factor_solve(RowState<NB> &st, float *U, float *
       if (t == 0) zb[8 * p + g] = bq;
     }
     __syncwarp();
-    // 2. 8x8 diagonal block, factored redundantly by every lane: U_d^T U_d = D, inv[r] = 1 / U_d[r][r]
-    float D[8][8], inv[8];
+    // 2. one panel column per lane (local column Wp is the rhs slice)
+    float v[NJmax][8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float4 lo = *reinterpret_cast<const float4 *>(Up + r * sp);
-      const float4 hi = *reinterpret_cast<const float4 *>(Up + r * sp + 4);
-      D[r][0] = lo.x; D[r][1] = lo.y; D[r][2] = lo.z; D[r][3] = lo.w;
-      D[r][4] = hi.x; D[r][5] = hi.y; D[r][6] = hi.z; D[r][7] = hi.w;
+    for (int j = 0; j < NJmax; ++j) {
+      if (j < NJ) {
+        const int c = lane + 32 * j;
+        const float *colp = (c < Wp) ? (Up + c) : (zb + 8 * p);
+        const int rs = (c < Wp) ? sp : 1;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[j][r] = (c <= Wp) ? colp[r * rs] : 0.f;
+      }
     }
+    // 3. eliminate the 8 pivots
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      float d = D[r][r];
-#pragma unroll
-      for (int q = 0; q < r; ++q) d = fmaf(-D[q][r], D[q][r], d);
-      ok = ok && (d > 0.f);
+      const float d = v[0][r];  // meaningful on lane r: the pivot
       float s = rsqrtf(d);
       s = s * fmaf(-0.5f * d * s, s, 1.5f);  // one Newton step: full fp32 accuracy
-      inv[r] = s;
+      const float inv = __shfl_sync(0xffffffffu, s, r);
 #pragma unroll
-      for (int c = r + 1; c < 8; ++c) {
-        float v = D[r][c];
+      for (int j = 0; j < NJmax; ++j)
+        if (j < NJ) v[j][r] *= inv;
+      if (lane == r) dinv[8 * p + r] = inv;
 #pragma unroll
-        for (int q = 0; q < r; ++q) v = fmaf(-D[q][r], D[q][c], v);
-        D[r][c] = v * s;
+      for (int r2 = r + 1; r2 < 8; ++r2) {
+        const float u = __shfl_sync(0xffffffffu, v[0][r], r2);  // U[r][8p + r2]
+#pragma unroll
+        for (int j = 0; j < NJmax; ++j)
+          if (j < NJ) v[j][r2] = fmaf(-u, v[j][r], v[j][r2]);
       }
     }
-    // 3. panel columns, one per lane: v <- U_d^-T v (local column Wp is the rhs slice in zb)
-    for (int c = lane; c <= Wp; c += 32) {
-      float *colp = (c < Wp) ? (Up + c) : (zb + 8 * p);
-      const int rs = (c < Wp) ? sp : 1;
-      float v[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = colp[r * rs];
+    for (int j = 0; j < NJmax; ++j) {
+      if (j < NJ) {
+        const int c = lane + 32 * j;
+        float *colp = (c < Wp) ? (Up + c) : (zb + 8 * p);
+        const int rs = (c < Wp) ? sp : 1;
+        if (c <= Wp) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        float a = v[r];
-#pragma unroll
-        for (int q = 0; q < r; ++q) a = fmaf(-D[q][r], v[q], a);
-        v[r] = (c == r) ? inv[r] : a * inv[r];  // the diagonal stores the reciprocal pivot
+          for (int r = 0; r < 8; ++r) colp[r * rs] = v[j][r];
+        }
       }
-#pragma unroll
-      for (int r = 0; r < 8; ++r) colp[r * rs] = v[r];
     }
     __syncwarp();
-    if (!ok) return false;
     // 4. trailing update in registers: A[m][n] -= sum_r U[r][m] U[r][n]; b[m] -= sum_r U[r][m] z[r]
     if (p + 1 < C::NT8) {
       const float z0 = zb[8 * p + t], z1 = zb[8 * p + t + 4];
@@ -239,27 +266,30 @@ __device__ __forceinline__ bool factor_solve(RowState<NB> &st, float *U, float *
         split_tf32(u1, uh1[j], ul1[j]);
       }
 #pragma unroll
-      for (int ib = (p + 1) >> 1; ib < NB; ++ib) {
-        // rows 16 ib + g (a0, a2) are still live only if 2 ib > p
-        const bool top = (2 * ib > p);
-        const uint32_t ah0 = top ? (uh0[top ? 2 * ib : p + 1] ^ kSignBit) : 0u;
-        const uint32_t al0 = top ? (ul0[top ? 2 * ib : p + 1] ^ kSignBit) : 0u;
-        const uint32_t ah2 = top ? (uh1[top ? 2 * ib : p + 1] ^ kSignBit) : 0u;
-        const uint32_t al2 = top ? (ul1[top ? 2 * ib : p + 1] ^ kSignBit) : 0u;
-        const uint32_t ah1 = uh0[2 * ib + 1] ^ kSignBit, al1 = ul0[2 * ib + 1] ^ kSignBit;
-        const uint32_t ah3 = uh1[2 * ib + 1] ^ kSignBit, al3 = ul1[2 * ib + 1] ^ kSignBit;
+      for (int term = 0; term < 3; ++term) {  // term-major, as in consume_kstep
 #pragma unroll
-        for (int j = (2 * ib > p + 1 ? 2 * ib : p + 1); j < C::NT8; ++j) {
-          float(&d)[4] = st.acc[C::tidx(ib, j)];
-          mma_tf32(d, al0, al1, al2, al3, uh0[j], uh1[j]);
-          mma_tf32(d, ah0, ah1, ah2, ah3, ul0[j], ul1[j]);
-          mma_tf32(d, ah0, ah1, ah2, ah3, uh0[j], uh1[j]);
+        for (int ib = (p + 1) >> 1; ib < NB; ++ib) {
+          // rows 16 ib + g (a0, a2) are still live only if 2 ib > p
+          const bool top = (2 * ib > p);
+          const int jt = top ? 2 * ib : p + 1;
+          const uint32_t a0 = top ? ((term == 0 ? ul0[jt] : uh0[jt]) ^ kSignBit) : 0u;
+          const uint32_t a2 = top ? ((term == 0 ? ul1[jt] : uh1[jt]) ^ kSignBit) : 0u;
+          const uint32_t a1 = (term == 0 ? ul0[2 * ib + 1] : uh0[2 * ib + 1]) ^ kSignBit;
+          const uint32_t a3 = (term == 0 ? ul1[2 * ib + 1] : uh1[2 * ib + 1]) ^ kSignBit;
+#pragma unroll
+          for (int j = (2 * ib > p + 1 ? 2 * ib : p + 1); j < C::NT8; ++j) {
+            float(&d)[4] = st.acc[C::tidx(ib, j)];
+            if (term == 1) mma_tf32(d, a0, a1, a2, a3, ul0[j], ul1[j]);
+            else mma_tf32(d, a0, a1, a2, a3, uh0[j], uh1[j]);
+          }
         }
       }
     }
   }
 
-  // 5. back substitution U x = z on the packed panels (column oriented: no reductions)
+  // 5. back substitution U x = z, column oriented and blocked by panel: lane m (and m + 32) owns z[m];
+  //    each panel's 8 unknowns are resolved in order (one shuffle + one multiply on the critical path),
+  //    then every earlier row folds the panel in with two 16-byte loads and 8 FMAs.
   constexpr int Q = (F + 31) / 32;
   float zz[Q], xx[Q];
   int rowoff[Q];
@@ -271,30 +301,62 @@ __device__ __forceinline__ bool factor_solve(RowState<NB> &st, float *U, float *
     // poff(pm) in closed form: 8 * sum_{s<pm} (F - 8 s + 8 [s even])
     const int po = 8 * (pm * F - 4 * pm * (pm - 1) + 8 * ((pm + 1) >> 1));
     const int ps = F - 8 * pm + ((pm & 1) ? 0 : 8);
-    rowoff[q] = po + (mm & 7) * ps - 8 * pm;
+    rowoff[q] = po + (mm & 7) * ps - 8 * pm;  // U[m][c] lives at U[rowoff + c] for c >= 8 pm
     zz[q] = zb[mm];
     xx[q] = 0.f;
   }
 #pragma unroll
-  for (int r = F - 1; r >= 0; --r) {
-    constexpr int unused = 0;
-    (void)unused;
-    const int pr = r >> 3;
-    const float invr = U[C::poff(pr) + (r & 7) * C::pstride(pr) + (r - 8 * pr)];
-    const float xr = __shfl_sync(0xffffffffu, zz[r >> 5], r & 31) * invr;
-    if (lane == (r & 31)) xx[r >> 5] = xr;
+  for (int p = C::NT8 - 1; p >= 0; --p) {
+    const int qp = (8 * p) >> 5;        // register slot of the panel's rows
+    const int l0 = (8 * p) & 31;        // their first lane
+    const float4 ia = *reinterpret_cast<const float4 *>(dinv + 8 * p);
+    const float4 ib4 = *reinterpret_cast<const float4 *>(dinv + 8 * p + 4);
+    const float inv[8] = {ia.x, ia.y, ia.z, ia.w, ib4.x, ib4.y, ib4.z, ib4.w};
+    // this lane's row of the diagonal block (meaningful on lanes l0..l0+7 of slot qp)
+    const float4 da = *reinterpret_cast<const float4 *>(U + rowoff[qp] + 8 * p);
+    const float4 db = *reinterpret_cast<const float4 *>(U + rowoff[qp] + 8 * p + 4);
+    const float ud[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+    const bool in_panel = (lane >= l0) && (lane < l0 + 8);
+    float xs[8];
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+      const float xr = __shfl_sync(0xffffffffu, zz[qp], l0 + r) * inv[r];
+      xs[r] = xr;
+      if (lane == l0 + r) xx[qp] = xr;
+      if (in_panel && lane < l0 + r) zz[qp] = fmaf(-ud[r], xr, zz[qp]);  // rows above r inside the panel
+    }
+    // rows before the panel
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-      const int m = lane + 32 * q;
-      if (m < r && 32 * q < r) zz[q] = fmaf(-U[rowoff[q] + r], xr, zz[q]);
+      if (32 * q < 8 * p) {
+        const int m = lane + 32 * q;
+        if (m < 8 * p) {
+          const float4 ua = *reinterpret_cast<const float4 *>(U + rowoff[q] + 8 * p);
+          const float4 ub = *reinterpret_cast<const float4 *>(U + rowoff[q] + 8 * p + 4);
+          float a = zz[q];
+          a = fmaf(-ua.x, xs[0], a); a = fmaf(-ua.y, xs[1], a); a = fmaf(-ua.z, xs[2], a); a = fmaf(-ua.w, xs[3], a);
+          a = fmaf(-ub.x, xs[4], a); a = fmaf(-ub.y, xs[5], a); a = fmaf(-ub.z, xs[6], a); a = fmaf(-ub.w, xs[7], a);
+          zz[q] = a;
+        }
+      }
     }
   }
+  bool fin = true;
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     const int m = lane + 32 * q;
-    if (m < F) xout[m] = xx[q];
+    if (m < F) {
+      fin = fin && (fabsf(xx[q]) <= 3.0e38f);  // false for inf and NaN
+    }
   }
-  return true;
+  ok = __all_sync(0xffffffffu, fin);
+  if (ok) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int m = lane + 32 * q;
+      if (m < F) xout[m] = xx[q];
+    }
+  }
 }
 
 // ---- kernel ------------------------------------------------------------------------------------
@@ -314,6 +376,7 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
   float *stages = wsm;
   float *U = wsm + C::NSTAGE * C::STAGE_FLOATS;
   float *zb = U + C::U_FLOATS;
+  float *dinv = zb + F;
 
   auto fetch = [&]() -> int {
     int v = 0;
@@ -325,21 +388,33 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
     const int4 v = __ldg(reinterpret_cast<const int4 *>(work) + i);
     return WorkItem{v.x, v.y, v.z, v.w};
   };
+  auto stage_ptr = [&](int s) -> float * { return stages + (s >= C::NSTAGE ? s - C::NSTAGE : s) * C::STAGE_FLOATS; };
+  const Blk kNoBlk{-1, 0.f};
 
-  int cur = fetch();
-  WorkItem wi{0, 0, 0, -1};
+  // software pipeline over work items: `wi` is being processed, `wn` (+ its first index block) is
+  // already in registers, the counter for the one after is fetched a whole row ahead
+  int i0 = fetch();
+  if (i0 < 0) return;
+  WorkItem wi = load_item(i0);
+  int i1 = fetch();
+  WorkItem wn{0, 0, 0, -1};
+  Blk b0 = kNoBlk, nb0 = kNoBlk;
   int stage = 0;
-  if (cur >= 0) {
-    wi = load_item(cur);
-    if (pass == 0) {
-      issue_kstep<NB>(stages + 0 * C::STAGE_FLOATS, wi, 0, indices, data, Y, lane);
-      issue_kstep<NB>(stages + 1 * C::STAGE_FLOATS, wi, 1, indices, data, Y, lane);
-    }
+  if (pass == 0) {
+    b0 = load_block(wi, 0, indices, data, lane);
+    const int nks0 = (wi.k1 - wi.k0 + 7) >> 3;
+    issue_kstep<NB>(stage_ptr(0), b0, 0, 0 < nks0, Y, lane);
+    issue_kstep<NB>(stage_ptr(1), b0, 1, 1 < nks0, Y, lane);
+  }
+  if (i1 >= 0) {
+    wn = load_item(i1);
+    if (pass == 0) nb0 = load_block(wn, 0, indices, data, lane);
   }
 
   RowState<NB> st;
-  while (cur >= 0) {
+  for (;;) {
     const bool whole = (wi.slot == -1), chunk = (wi.slot >= 0), finish = (wi.slot == -2);
+    const int i2 = (i1 >= 0) ? fetch() : -1;  // consumed after this row's accumulation
     // ---- initialise the accumulators: Y^T Y + lambda I for a row that will be solved, 0 for a chunk
 #pragma unroll
     for (int c = 0; c < C::NT8; ++c) st.bp[c] = 0.f;
@@ -357,28 +432,34 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
         }
       }
 
-    int nxt = -1;
-    WorkItem wn{0, 0, 0, -1};
+    WorkItem wnn{0, 0, 0, -1};
+    Blk nnb0 = kNoBlk;
     if (pass == 0) {
       const int nks = (wi.k1 - wi.k0 + 7) >> 3;
+      Blk cb = b0;
+      Blk nb = (nks > 4) ? load_block(wi, 1, indices, data, lane) : kNoBlk;
       for (int ks = 0; ks < nks; ++ks) {
         cp_async_wait<1>();
         __syncwarp();
-        int s2 = stage + 2;
-        if (s2 >= C::NSTAGE) s2 -= C::NSTAGE;
-        issue_kstep<NB>(stages + s2 * C::STAGE_FLOATS, wi, ks + 2, indices, data, Y, lane);
-        consume_kstep<NB>(st, stages + stage * C::STAGE_FLOATS, g, t);
+        const int tks = ks + 2;
+        if ((tks & 3) == 0 && tks < nks) {  // the gathers move on to the next 32 nonzeros
+          cb = nb;
+          if (tks + 4 < nks) nb = load_block(wi, (tks >> 2) + 1, indices, data, lane);
+        }
+        issue_kstep<NB>(stage_ptr(stage + 2), cb, tks & 3, tks < nks, Y, lane);
+        consume_kstep<NB>(st, stage_ptr(stage), g, t);
         if (++stage == C::NSTAGE) stage = 0;
       }
-      // prefetch the first two k-steps of the next item; they land while this row is factored
-      nxt = fetch();
       __syncwarp();
-      if (nxt >= 0) {
-        wn = load_item(nxt);
-        int s1 = stage + 1;
-        if (s1 >= C::NSTAGE) s1 -= C::NSTAGE;
-        issue_kstep<NB>(stages + stage * C::STAGE_FLOATS, wn, 0, indices, data, Y, lane);
-        issue_kstep<NB>(stages + s1 * C::STAGE_FLOATS, wn, 1, indices, data, Y, lane);
+      // the first two k-steps of the next item land while this row is factored
+      if (i1 >= 0) {
+        const int nks1 = (wn.k1 - wn.k0 + 7) >> 3;
+        issue_kstep<NB>(stage_ptr(stage), nb0, 0, 0 < nks1, Y, lane);
+        issue_kstep<NB>(stage_ptr(stage + 1), nb0, 1, 1 < nks1, Y, lane);
+      }
+      if (i2 >= 0) {
+        wnn = load_item(i2);
+        nnb0 = load_block(wnn, 0, indices, data, lane);
       }
     } else {
       // finish: add the chunk partials in slot order
@@ -391,8 +472,7 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
 #pragma unroll
         for (int c = 0; c < C::NT8; ++c) st.bp[c] += sl[(C::NTILES * 4 + c) * 32 + lane];
       }
-      nxt = fetch();
-      if (nxt >= 0) wn = load_item(nxt);
+      if (i2 >= 0) wnn = load_item(i2);
     }
 
     if (chunk) {
@@ -409,13 +489,18 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
         // no observations: the reference zeroes the row (_als.pyx:98-100)
         for (int m = lane; m < F; m += 32) xout[m] = 0.f;
       } else if (whole || finish) {
-        const bool ok = factor_solve<NB>(st, U, zb, xout, lane);
+        bool ok = true;
+        factor_solve<NB>(st, U, zb, dinv, xout, lane, ok);
         if (!ok && lane == 0) atomicMin(bad_row, (long long)(row_offset + wi.row));
         __syncwarp();
       }
     }
-    cur = nxt;
+    if (i1 < 0) break;
     wi = wn;
+    b0 = nb0;
+    i1 = i2;
+    wn = wnn;
+    nb0 = nnb0;
   }
   cp_async_wait<0>();
 }
