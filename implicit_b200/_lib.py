@@ -53,6 +53,7 @@ SIGNATURES = {
     "als_factors_upload": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64]),
     "als_factors_download": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64]),
     "als_factors_shape": (c_int, [c_void_p, P(c_i64), P(c_int), P(c_int)]),
+    "als_factors_has_nan": (c_int, [c_void_p, c_void_p, P(c_int)]),
     "als_factors_destroy": (c_int, [c_void_p]),
     "als_gramian": (c_int, [c_void_p, c_void_p, c_void_p]),
     "als_least_squares": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
@@ -198,30 +199,28 @@ class Context:
         check(self.lib.als_comm_barrier(self.h))
 
 
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            load().als_host_free(self.ptr)
+        except Exception:  # interpreter shutdown
+            pass
+
+
 def pinned_empty(shape, dtype):
-    """numpy array backed by page-locked host memory (freed with the returned array's base object)."""
+    """numpy array backed by page-locked host memory (cudaMallocHost): H2D / D2H copies of it run at
+    full PCIe speed.  The memory is released when the last view of the array dies."""
     dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
+    count = int(np.prod(shape))
+    n = count * dtype.itemsize
     p = c_void_p()
     check(load().als_host_alloc(ctypes.byref(p), n))
     buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                load().als_host_free(self.ptr)
-            except Exception:
-                pass
-
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED_OWNERS[id(buf)] = (buf, _Owner(p))
-    return arr
-
-
-_PINNED_OWNERS = {}
+    buf._owner = _PinnedOwner(p)  # numpy keeps `buf` alive as the base of every view
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
 def comm_unique_id():
@@ -319,9 +318,14 @@ class DeviceFactors:
         assert a.ndim == 2 and a.shape[1] == self.factors
         check(self.ctx.lib.als_factors_upload(self.ctx.h, self.h, ptr(a), int(row0), a.shape[0]))
 
-    def download(self, row0=0, nrows=None):
+    def has_nan(self):
+        flag = c_int(0)
+        check(self.ctx.lib.als_factors_has_nan(self.ctx.h, self.h, ctypes.byref(flag)))
+        return bool(flag.value)
+
+    def download(self, row0=0, nrows=None, pinned=False):
         nrows = self.rows - row0 if nrows is None else nrows
-        out = np.empty((nrows, self.factors), dtype=np.float32)
+        out = (pinned_empty if pinned else np.empty)((nrows, self.factors), dtype=np.float32)
         check(self.ctx.lib.als_factors_download(self.ctx.h, self.h, ptr(out), int(row0), int(nrows)))
         return out
 

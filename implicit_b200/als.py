@@ -87,7 +87,7 @@ class AlternatingLeastSquares:
     def _get_host(self, side):
         host = self._user_factors if side == "user" else self._item_factors
         if not self._host_fresh[side] and self._dev[side] is not None:
-            host = self._dev[side].download()
+            host = self._dev[side].download(pinned=True)  # page-locked: the D2H copy runs at PCIe speed
             if side == "user":
                 self._user_factors = host
             else:
@@ -230,8 +230,8 @@ class AlternatingLeastSquares:
         return float((t[0] + t[2]) / (t[1] + float(users) * float(items) - float(nnz)))
 
     def _check_fit_errors(self):
-        """implicit/recommender_base.py:218-223"""
-        is_nan = bool(np.any(np.isnan(self.user_factors))) or bool(np.any(np.isnan(self.item_factors)))
+        """implicit/recommender_base.py:218-223 (the NaN scan runs on the device replicas)"""
+        is_nan = self._device_factors("user").has_nan() or self._device_factors("item").has_nan()
         if is_nan:
             raise ModelFitError("NaN encountered in factors")
 

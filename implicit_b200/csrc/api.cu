@@ -57,6 +57,8 @@ int ensure_pinned(als_ctx *ctx, int64_t bytes) {
 int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr) {
   std::vector<WorkItem> items;
   std::vector<WorkItem> fin;
+  std::vector<WorkItem> chunks;
+  std::vector<int32_t> owner;
   items.reserve((size_t)csr->rows + 64);
   int64_t slots = 0;
   for (int64_t r = 0; r < csr->rows; ++r) {
@@ -69,6 +71,8 @@ int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr) {
         const int32_t k0 = b + c * kChunkNnz;
         const int32_t k1 = std::min(e, k0 + kChunkNnz);
         items.push_back(WorkItem{(int32_t)r, k0, k1, (int32_t)slots});
+        chunks.push_back(items.back());
+        owner.push_back((int32_t)fin.size() - 1);
         ++slots;
       }
     } else {
@@ -102,6 +106,14 @@ int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr) {
     ALS_CUDA(cudaMemcpyAsync(csr->finish, fin.data(), sizeof(WorkItem) * fin.size(), cudaMemcpyHostToDevice,
                              ctx->stream));
   }
+  if (!chunks.empty()) {
+    ALS_CUDA(cudaMalloc(&csr->chunks, sizeof(WorkItem) * chunks.size()));
+    ALS_CUDA(cudaMalloc(&csr->chunk_owner, sizeof(int32_t) * owner.size()));
+    ALS_CUDA(cudaMemcpyAsync(csr->chunks, chunks.data(), sizeof(WorkItem) * chunks.size(), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    ALS_CUDA(cudaMemcpyAsync(csr->chunk_owner, owner.data(), sizeof(int32_t) * owner.size(), cudaMemcpyHostToDevice,
+                             ctx->stream));
+  }
   ALS_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vectors die here
   return ALS_OK;
 }
@@ -124,6 +136,14 @@ ProfScope::~ProfScope() {
     cudaEventDestroy(ctx->prof_events[which].back());
     ctx->prof_events[which].pop_back();
   }
+}
+
+__global__ void has_nan_kernel(const float *data, int64_t n, int *flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < n; i += stride) bad |= isnan(data[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 __global__ void scale_kernel(float *data, int64_t n, float alpha) {
@@ -424,6 +444,8 @@ ALS_API int als_csr_destroy(als_csr *csr) {
   }
   cudaFree(csr->work);
   cudaFree(csr->finish);
+  cudaFree(csr->chunks);
+  cudaFree(csr->chunk_owner);
   delete csr;
   return ALS_OK;
 }
@@ -468,6 +490,19 @@ ALS_API int als_factors_download(als_ctx *ctx, const als_factors *f, float *host
   ALS_CUDA(cudaSetDevice(ctx->device));
   ALS_CUDA(cudaMemcpy2DAsync(host, sizeof(float) * f->f, f->d + row0 * f->ld, sizeof(float) * f->ld,
                              sizeof(float) * f->f, nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ALS_OK;
+}
+
+ALS_API int als_factors_has_nan(als_ctx *ctx, const als_factors *f, int *has_nan) {
+  ALS_REQUIRE(ctx && f && has_nan, "als_factors_has_nan: NULL argument");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  int *flag = reinterpret_cast<int *>(ctx->counters + 8);
+  ALS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+  has_nan_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(f->d, f->rows * (int64_t)f->ld, flag);
+  ALS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  ALS_CUDA(cudaMemcpyAsync(has_nan, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   ALS_CUDA(cudaStreamSynchronize(ctx->stream));
   return ALS_OK;
 }

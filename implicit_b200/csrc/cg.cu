@@ -1,28 +1,40 @@
 // R2: fused conjugate-gradient half-iteration (reference: _least_squares_cg, implicit/cpu/_als.pyx:154-248;
 // the reference's own GPU kernel is least_squares_cg_kernel, implicit/gpu/als.cu:23-111).
-// R6: training loss (reference: _calculate_loss, implicit/cpu/_als.pyx:259-308).
 //
 // Matrix-free CG, (1 + cg_steps) passes over the row's nonzeros.  A warp owns a row; inside the warp
-// sub-groups of L = F/4 lanes each take one nonzero at a time: lane `sub` of a group holds the
-// float4 slice [4 sub, 4 sub + 4) of every CG vector (x, r, p, Ap are replicated per group), so a
-// factor row is read with one coalesced 16-byte load per lane and a dot product costs log2(L)
-// shuffles.  Giant rows (more than kSplitNnz nonzeros) are handled by a whole CTA per row with a
-// fixed-order cross-warp reduction, so a power-law hub cannot serialise the tail.
+// groups of L = F/16 lanes (padded to a power of two) each take one nonzero at a time.  A lane holds
+// 16 floats (four float4, interleaved so that a group's lanes read consecutive 16-byte words) of every
+// CG vector -- x, r, p, Ap are replicated per group -- so a factor row costs four coalesced loads per
+// lane and a dot product only log2(L) shuffles: at F = 64 eight nonzeros are in flight per warp
+// instruction and a dot costs 2 shuffles (the first version, one float4 per lane, spent more issue
+// slots on shuffles than on FMAs).
+//
+// Rows with more than kSplitNnz nonzeros ("giant" rows: the 139k-nnz hub item of C2) are not walked by
+// one warp: every pass is split over their 2048-nonzero chunks (one warp each, partial sums to scratch)
+// and a one-warp-per-row kernel combines the chunk sums in slot order and advances the CG recurrences,
+// i.e. 2 (1 + cg_steps) short launches per half-iteration, deterministic.
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace als {
 
 namespace {
 
-constexpr int kCgWarps = 8;        // warps per CTA, warp-per-row kernel
-constexpr int kCgGiantWarps = 16;  // warps per CTA, CTA-per-row kernel
+constexpr int kCgWarps = 8;  // warps per CTA
 
-template <int F>
+template <int F, int NV>
 struct CgCfg {
-  static constexpr int V = F / 4;  // float4 slices per factor row
-  static constexpr int L = V <= 4 ? 4 : V <= 8 ? 8 : V <= 16 ? 16 : 32;  // lanes per group
-  static constexpr int NG = 32 / L;                                     // groups per warp
-  static_assert(V <= 32, "CG kernel handles padded factors <= 128");
+  static constexpr int V = F / 4;                    // float4 words per factor row
+  static constexpr int LR = (V + NV - 1) / NV;       // lanes really needed per row
+  static constexpr int L = LR <= 1 ? 1 : LR <= 2 ? 2 : LR <= 4 ? 4 : LR <= 8 ? 8 : LR <= 16 ? 16 : 32;  // lanes per group
+  static constexpr int NG = 32 / L;                  // groups (nonzeros in flight) per warp
+  static_assert(F % 16 == 0 && F <= 128 && LR <= 32, "CG kernel handles padded factors <= 128");
+};
+
+template <int NV>
+struct VecT {  // this lane's 4 NV floats of an F-vector: float4 words sub + L*i, i = 0..NV-1
+  float4 v[NV];
 };
 
 __device__ __forceinline__ float dot4(const float4 &a, const float4 &b) {
@@ -31,381 +43,368 @@ __device__ __forceinline__ float dot4(const float4 &a, const float4 &b) {
 __device__ __forceinline__ void axpy4(float4 &y, float a, const float4 &x) {
   y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z); y.w = fmaf(a, x.w, y.w);
 }
+__device__ __forceinline__ void add4(float4 &a, const float4 &b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 __device__ __forceinline__ float4 shfl_xor4(const float4 &v, int m) {
   return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
                      __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
 }
-__device__ __forceinline__ void add4(float4 &a, const float4 &b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
-// sum over the L lanes of a group (all lanes of the group get the same bits)
-template <int L>
-__device__ __forceinline__ float group_sum(float v) {
+template <int F, int NV>
+struct Lane {
+  using C = CgCfg<F, NV>;
+  using Vec = VecT<NV>;
+  int lane, sub, grp;
+  float *xs;  // per-warp F floats: broadcast buffer for the symv
+
+  __device__ __forceinline__ bool ok(int i) const { return sub + C::L * i < C::V; }
+
+  __device__ __forceinline__ Vec zero() const {
+    Vec r;
 #pragma unroll
-  for (int m = 1; m < L; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  return v;
-}
-// sum a per-group float4 over the NG groups of the warp
-template <int L>
-__device__ __forceinline__ void across_groups(float4 &v) {
+    for (int i = 0; i < NV; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+  }
+  __device__ __forceinline__ Vec load(const float *__restrict__ row, bool pred = true) const {
+    Vec r;
 #pragma unroll
-  for (int m = L; m < 32; m <<= 1) add4(v, shfl_xor4(v, m));
-}
-
-// Team = the warps that cooperate on one row (1 for the warp-per-row kernel, the CTA for giants).
-template <int F, int TW>
-struct Team {
-  using C = CgCfg<F>;
-  int lane, sub, grp, warp;  // warp = index inside the team
-  bool active;
-  float *xs;    // per-warp F floats: vector broadcast for the symv
-  float *red;   // TW > 1: [TW][F] cross-warp reduction buffer
-
-  // out = G v  (G symmetric F x F, row-major, L1/L2 resident).  v is replicated in every group.
-  __device__ __forceinline__ float4 symv(const float *__restrict__ G, const float4 &v) const {
-    if (grp == 0 && active) reinterpret_cast<float4 *>(xs)[sub] = v;
-    __syncwarp();
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-      for (int j = 4 * grp; j < F; j += 4 * C::NG) {
-        const float4 xv = *reinterpret_cast<const float4 *>(xs + j);
-        axpy4(acc, xv.x, __ldg(reinterpret_cast<const float4 *>(G + (j + 0) * F) + sub));
-        axpy4(acc, xv.y, __ldg(reinterpret_cast<const float4 *>(G + (j + 1) * F) + sub));
-        axpy4(acc, xv.z, __ldg(reinterpret_cast<const float4 *>(G + (j + 2) * F) + sub));
-        axpy4(acc, xv.w, __ldg(reinterpret_cast<const float4 *>(G + (j + 3) * F) + sub));
-      }
+    for (int i = 0; i < NV; ++i)
+      r.v[i] = (pred && ok(i)) ? __ldg(reinterpret_cast<const float4 *>(row) + sub + C::L * i)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+  }
+  __device__ __forceinline__ Vec load_rw(const float *row) const {  // data written by a previous kernel/this one
+    Vec r;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      r.v[i] = ok(i) ? reinterpret_cast<const float4 *>(row)[sub + C::L * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+  }
+  __device__ __forceinline__ void store(float *row, const Vec &a) const {  // group 0 writes
+    if (grp == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (ok(i)) reinterpret_cast<float4 *>(row)[sub + C::L * i] = a.v[i];
     }
-    across_groups<C::L>(acc);
+  }
+  // sum over the L lanes of a group (every lane of the group gets the same bits)
+  __device__ __forceinline__ float gsum(float v) const {
+#pragma unroll
+    for (int m = 1; m < C::L; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+  }
+  __device__ __forceinline__ float dot(const Vec &a, const Vec &b) const {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += dot4(a.v[i], b.v[i]);
+    return gsum(s);
+  }
+  // sum a per-group Vec over the NG groups of the warp (identical bits in every group afterwards)
+  __device__ __forceinline__ void across_groups(Vec &a) const {
+#pragma unroll
+    for (int m = C::L; m < 32; m <<= 1)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) add4(a.v[i], shfl_xor4(a.v[i], m));
+  }
+  // out = G a  (G symmetric F x F, row-major, L1/L2 resident); a is replicated in every group
+  __device__ __forceinline__ Vec symv(const float *__restrict__ G, const Vec &a) const {
+    if (grp == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (ok(i)) reinterpret_cast<float4 *>(xs)[sub + C::L * i] = a.v[i];
+    }
+    __syncwarp();
+    Vec acc = zero();
+    for (int j = grp; j < F; j += C::NG) {
+      const float aj = xs[j];
+      const float4 *row = reinterpret_cast<const float4 *>(G + j * F);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (ok(i)) axpy4(acc.v[i], aj, __ldg(row + sub + C::L * i));
+    }
+    across_groups(acc);
     __syncwarp();
     return acc;
   }
-
-  // total over every group of every warp of the team; identical bits in all lanes of the team
-  __device__ __forceinline__ void team_sum(float4 &v) const {
-    across_groups<C::L>(v);
-    if (TW > 1) {
-      if (grp == 0 && active) reinterpret_cast<float4 *>(red + warp * F)[sub] = v;
-      __syncthreads();
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (active)
-        for (int w = 0; w < TW; ++w) add4(s, reinterpret_cast<const float4 *>(red + w * F)[sub]);
-      __syncthreads();
-      v = s;
+  // One pass over the nonzeros [k0, k1):  acc += coef_k y_k,  coef_k = pos_k - sign (|c_k| - 1) (y_k . a)
+  // with pos_k = c_k if (FIRST and c_k > 0) else 0                  (_als.pyx:190-201 and :214-222).
+  // `gid` of `tg` groups take every tg-th nonzero; the trip count is warp-uniform.
+  template <bool FIRST>
+  __device__ __forceinline__ Vec nnz_pass(const int32_t *__restrict__ indices, const float *__restrict__ data,
+                                          const float *__restrict__ Y, int k0, int k1, const Vec &a, float sign,
+                                          int gid, int tg) const {
+    Vec acc = zero();
+    constexpr int UN = NV >= 4 ? 2 : 4;
+    for (int kb = k0; kb < k1; kb += UN * tg) {
+      Vec y[UN];
+      float c[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int k = kb + u * tg + gid;
+        const bool valid = k < k1;
+        const int idx = valid ? __ldg(indices + k) : 0;
+        c[u] = valid ? __ldg(data + k) : 0.f;
+        y[u] = load(Y + (int64_t)idx * F, valid);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const float d = dot(y[u], a);
+        const float conf = fabsf(c[u]);
+        const float pos = (FIRST && c[u] > 0.f) ? c[u] : 0.f;
+        const float coef = pos - sign * (conf - 1.f) * d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) axpy4(acc.v[i], coef, y[u].v[i]);  // masked nonzeros have y == 0
+      }
     }
+    return acc;
   }
 };
 
-// One pass over the nonzeros [k0, k1):  acc += coef_k * y_k  with coef_k = pos_k - (|c_k| - 1) (y_k . v)
-// where pos_k = c_k if (first pass and c_k > 0) else 0.   (_als.pyx:190-201 and :214-222)
-template <int F, int TW, bool FIRST>
-__device__ __forceinline__ float4 nnz_pass(const Team<F, TW> &tm, const int32_t *__restrict__ indices,
-                                           const float *__restrict__ data, const float *__restrict__ Y, int k0, int k1,
-                                           const float4 &v, float sign) {
-  using C = CgCfg<F>;
-  constexpr int TG = TW * C::NG;
-  const int gid = tm.warp * C::NG + tm.grp;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  constexpr int UN = 4;
-  // The trip count must be uniform across the warp (the group reductions are full-warp shuffles):
-  // every group walks the same kb and masks its own out-of-range nonzeros to y = 0.
-  for (int kb = k0; kb < k1; kb += UN * TG) {
-    float4 y[UN];
-    float c[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int k = kb + u * TG + gid;
-      const bool valid = k < k1;
-      const int idx = valid ? __ldg(indices + k) : 0;
-      c[u] = valid ? __ldg(data + k) : 0.f;
-      y[u] = (tm.active && valid) ? __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx * F) + tm.sub)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const float d = group_sum<C::L>(dot4(y[u], v));
-      const float conf = fabsf(c[u]);
-      const float pos = (FIRST && c[u] > 0.f) ? c[u] : 0.f;
-      const float coef = pos - sign * (conf - 1.f) * d;
-      axpy4(acc, coef, y[u]);  // masked nonzeros have y == 0
-    }
-  }
-  return acc;
+template <int F, int NV>
+__device__ __forceinline__ Lane<F, NV> make_lane(float *xs_all) {
+  Lane<F, NV> ln;
+  ln.lane = threadIdx.x & 31;
+  ln.sub = ln.lane % CgCfg<F, NV>::L;
+  ln.grp = ln.lane / CgCfg<F, NV>::L;
+  ln.xs = xs_all + (threadIdx.x >> 5) * F;
+  return ln;
 }
 
-template <int F, int TW>
-__device__ __forceinline__ void cg_row(const Team<F, TW> &tm, const int32_t *__restrict__ indices,
-                                       const float *__restrict__ data, const float *__restrict__ Y,
-                                       float *__restrict__ xrow, const float *__restrict__ Greg, int k0, int k1,
-                                       int cg_steps) {
-  using C = CgCfg<F>;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (k0 == k1) {  // no observations: zero the row (_als.pyx:182-184)
-    if (tm.warp == 0 && tm.grp == 0 && tm.active) reinterpret_cast<float4 *>(xrow)[tm.sub] = zero4;
-    return;
-  }
-  float4 x = tm.active ? reinterpret_cast<const float4 *>(xrow)[tm.sub] : zero4;  // warm start (:179)
-  // r = -(YtY + lambda I) x + sum_k (c_k^+ - (|c_k| - 1) y_k.x) y_k      (:187-201)
-  float4 r = tm.symv(Greg, x);
-  r.x = -r.x; r.y = -r.y; r.z = -r.z; r.w = -r.w;
-  {
-    float4 a = nnz_pass<F, TW, true>(tm, indices, data, Y, k0, k1, x, 1.f);
-    tm.team_sum(a);
-    add4(r, a);
-  }
-  float4 p = r;
-  float rsold = group_sum<C::L>(dot4(r, r));
-  if (rsold < 1e-20f) return;  // :206-207 (x stays as it is)
-  for (int it = 0; it < cg_steps; ++it) {
-    // Ap = (YtY + lambda I) p + sum_k (|c_k| - 1) (y_k.p) y_k           (:212-222)
-    float4 Ap = tm.symv(Greg, p);
-    {
-      float4 a = nnz_pass<F, TW, false>(tm, indices, data, Y, k0, k1, p, -1.f);
-      tm.team_sum(a);
-      add4(Ap, a);
-    }
-    const float alpha = rsold / group_sum<C::L>(dot4(p, Ap));  // :225
-    axpy4(x, alpha, p);                                       // :228
-    axpy4(r, -alpha, Ap);                                     // :231-232
-    const float rsnew = group_sum<C::L>(dot4(r, r));          // :234
-    if (rsnew < 1e-20f) break;                                // :235-236
-    const float beta = rsnew / rsold;                         // :239-242
-    p.x = fmaf(beta, p.x, r.x); p.y = fmaf(beta, p.y, r.y); p.z = fmaf(beta, p.z, r.z); p.w = fmaf(beta, p.w, r.w);
-    rsold = rsnew;
-  }
-  if (tm.warp == 0 && tm.grp == 0 && tm.active) reinterpret_cast<float4 *>(xrow)[tm.sub] = x;
-}
-
-template <int F>
+// ---- whole rows: one warp per row --------------------------------------------------------------
+template <int F, int NV>
 __global__ void __launch_bounds__(32 * kCgWarps)
-cg_half_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
+cg_rows_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
                float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
                const WorkItem *__restrict__ work, int n_work, int32_t *counter, int cg_steps) {
-  using C = CgCfg<F>;
-  __shared__ __align__(16) float xs_all[kCgWarps][F];
-  Team<F, 1> tm;
-  tm.lane = threadIdx.x & 31;
-  tm.sub = tm.lane % C::L;
-  tm.grp = tm.lane / C::L;
-  tm.warp = 0;
-  tm.active = tm.sub < C::V;
-  tm.xs = xs_all[threadIdx.x >> 5];
-  tm.red = nullptr;
+  using C = CgCfg<F, NV>;
+  using Vec = VecT<NV>;
+  __shared__ __align__(16) float xs_all[kCgWarps * F];
+  const Lane<F, NV> ln = make_lane<F, NV>(xs_all);
   for (;;) {
-    int i = 0;
-    if (tm.lane == 0) i = atomicAdd(counter, 1);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= n_work) break;
-    const int4 w = __ldg(reinterpret_cast<const int4 *>(work) + i);
-    if (w.w != -1) continue;  // chunks of giant rows: the CTA-per-row kernel owns those rows
-    cg_row<F, 1>(tm, indices, data, Y, X + (row_offset + w.x) * F, Greg, w.y, w.z, cg_steps);
-  }
-}
-
-template <int F>
-__global__ void __launch_bounds__(32 * kCgGiantWarps)
-cg_giant_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
-                const float *__restrict__ Y, float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
-                const WorkItem *__restrict__ finish, int n_finish, int cg_steps) {
-  using C = CgCfg<F>;
-  __shared__ __align__(16) float xs_all[kCgGiantWarps][F];
-  __shared__ __align__(16) float red[kCgGiantWarps][F];
-  Team<F, kCgGiantWarps> tm;
-  tm.lane = threadIdx.x & 31;
-  tm.sub = tm.lane % C::L;
-  tm.grp = tm.lane / C::L;
-  tm.warp = threadIdx.x >> 5;
-  tm.active = tm.sub < C::V;
-  tm.xs = xs_all[tm.warp];
-  tm.red = &red[0][0];
-  for (int i = blockIdx.x; i < n_finish; i += gridDim.x) {
-    const int row = finish[i].row;
-    cg_row<F, kCgGiantWarps>(tm, indices, data, Y, X + (row_offset + row) * F, Greg, indptr[row], indptr[row + 1],
-                             cg_steps);
-    __syncthreads();
-  }
-}
-
-// ---- loss --------------------------------------------------------------------------------------
-// loss numerator = sum_u x_u^T (Y^T Y) x_u + sum_k [(-2 c_k^+ + (|c_k| - 1) d_k) d_k + |c_k|],  d_k = y_k . x_u
-// (expanding r.x in _als.pyx:282-300); the quadratic term is <Y^T Y, X^T X>_F and the norms are the
-// traces of the two Gramians, so only the per-nonzero term needs the CSR.
-template <int F>
-__global__ void __launch_bounds__(256)
-loss_nnz_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
-                const float *__restrict__ X, int64_t row_offset, const WorkItem *__restrict__ work, int n_work,
-                int32_t *counter, double *out /* [0]=term sum, [1]=sum |c| */) {
-  using C = CgCfg<F>;
-  const int lane = threadIdx.x & 31, sub = lane % C::L, grp = lane / C::L;
-  const bool active = sub < C::V;
-  double term = 0.0, conf_sum = 0.0;
-  for (;;) {
-    int i = 0;
-    if (lane == 0) i = atomicAdd(counter, 1);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= n_work) break;
-    const int4 w = __ldg(reinterpret_cast<const int4 *>(work) + i);
-    if (w.w == -2) continue;
-    const float4 x = active ? __ldg(reinterpret_cast<const float4 *>(X + (row_offset + w.x) * F) + sub)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int kb = w.y; kb < w.z; kb += C::NG) {  // uniform trip count: full-warp shuffles inside
-      const int k = kb + grp;
-      const bool valid = k < w.z;
-      const int idx = valid ? __ldg(indices + k) : 0;
-      const float c = valid ? __ldg(data + k) : 0.f;
-      const float4 y = (active && valid) ? __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx * F) + sub)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float d = group_sum<C::L>(dot4(y, x));
-      const float conf = fabsf(c);
-      const float temp = (c > 0.f ? -2.f * c : 0.f) + (conf - 1.f) * d;
-      if (sub == 0 && valid) {
-        term += (double)(temp * d) + (double)conf;
-        conf_sum += (double)conf;
+    int it = 0;
+    if (ln.lane == 0) it = atomicAdd(counter, 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= n_work) break;
+    const int4 w = __ldg(reinterpret_cast<const int4 *>(work) + it);
+    if (w.w != -1) continue;  // chunks of giant rows: handled by the chunk / combine kernels
+    float *xrow = X + (row_offset + w.x) * F;
+    const int k0 = w.y, k1 = w.z;
+    if (k0 == k1) {  // no observations: zero the row (_als.pyx:182-184)
+      ln.store(xrow, ln.zero());
+      continue;
+    }
+    Vec x = ln.load_rw(xrow);  // warm start (:179)
+    // r = -(YtY + lambda I) x + sum_k (c_k^+ - (|c_k| - 1) y_k.x) y_k      (:187-201)
+    Vec r = ln.symv(Greg, x);
+    {
+      Vec a = ln.template nnz_pass<true>(indices, data, Y, k0, k1, x, 1.f, ln.grp, C::NG);
+      ln.across_groups(a);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        r.v[i].x = a.v[i].x - r.v[i].x; r.v[i].y = a.v[i].y - r.v[i].y;
+        r.v[i].z = a.v[i].z - r.v[i].z; r.v[i].w = a.v[i].w - r.v[i].w;
       }
     }
-  }
-  // warp reduce then one atomic per warp
+    Vec p = r;
+    float rsold = ln.dot(r, r);
+    if (rsold < 1e-20f) continue;  // :206-207 (x stays as it is)
+    for (int s = 0; s < cg_steps; ++s) {
+      // Ap = (YtY + lambda I) p + sum_k (|c_k| - 1) (y_k.p) y_k           (:212-222)
+      Vec Ap = ln.symv(Greg, p);
+      {
+        Vec a = ln.template nnz_pass<false>(indices, data, Y, k0, k1, p, -1.f, ln.grp, C::NG);
+        ln.across_groups(a);
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) {
-    term += __shfl_xor_sync(0xffffffffu, term, m);
-    conf_sum += __shfl_xor_sync(0xffffffffu, conf_sum, m);
-  }
-  if (lane == 0) {
-    atomicAdd(out + 0, term);
-    atomicAdd(out + 1, conf_sum);
-  }
-}
-
-// out[2] = <A, B>_F, out[3] = trace(A), out[4] = trace(B) over the f x f leading blocks
-__global__ void frob_trace_kernel(const float *__restrict__ A, const float *__restrict__ B, int f, int ld, double *out) {
-  __shared__ double sh[3][256];
-  double s = 0.0, ta = 0.0, tb = 0.0;
-  for (int e = threadIdx.x; e < f * f; e += blockDim.x) {
-    const int i = e / f, j = e % f;
-    s += (double)A[i * ld + j] * (double)B[i * ld + j];
-    if (i == j) {
-      ta += A[i * ld + j];
-      tb += B[i * ld + j];
+        for (int i = 0; i < NV; ++i) add4(Ap.v[i], a.v[i]);
+      }
+      const float alpha = rsold / ln.dot(p, Ap);  // :225
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        axpy4(x.v[i], alpha, p.v[i]);    // :228
+        axpy4(r.v[i], -alpha, Ap.v[i]);  // :231-232
+      }
+      const float rsnew = ln.dot(r, r);  // :234
+      if (rsnew < 1e-20f) break;         // :235-236
+      const float beta = rsnew / rsold;  // :239-242
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        p.v[i].x = fmaf(beta, p.v[i].x, r.v[i].x); p.v[i].y = fmaf(beta, p.v[i].y, r.v[i].y);
+        p.v[i].z = fmaf(beta, p.v[i].z, r.v[i].z); p.v[i].w = fmaf(beta, p.v[i].w, r.v[i].w);
+      }
+      rsold = rsnew;
     }
-  }
-  sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = ta; sh[2][threadIdx.x] = tb;
-  __syncthreads();
-  for (int m = 128; m > 0; m >>= 1) {
-    if (threadIdx.x < m)
-      for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + m];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    out[2] = sh[0][0]; out[3] = sh[1][0]; out[4] = sh[2][0];
+    ln.store(xrow, x);
   }
 }
 
-__global__ void zero_scalars(int32_t *counters, double *d) {
+// ---- giant rows: chunk pass + per-row combine ------------------------------------------------------
+// state per giant row g (index into the finish list): rst[g][F], pst[g][F], scal[g] = {rsold, done}
+template <int F, int NV>
+__global__ void __launch_bounds__(32 * kCgWarps)
+cg_chunk_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
+                const float *X, int64_t row_offset, const WorkItem *__restrict__ chunks,
+                const int32_t *__restrict__ owner, int n_chunks, const float *pst, const float *scal,
+                float *partials, int first) {
+  using C = CgCfg<F, NV>;
+  using Vec = VecT<NV>;
+  __shared__ __align__(16) float xs_all[kCgWarps * F];
+  const Lane<F, NV> ln = make_lane<F, NV>(xs_all);
+  const int warp_global = blockIdx.x * kCgWarps + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * kCgWarps;
+  for (int ci = warp_global; ci < n_chunks; ci += nwarps) {
+    const WorkItem w = chunks[ci];
+    const int g = owner[ci];
+    if (!first && scal[2 * g + 1] != 0.f) continue;  // this row's CG already stopped
+    const Vec a = first ? ln.load_rw(X + (row_offset + w.row) * F) : ln.load_rw(pst + (int64_t)g * F);
+    Vec acc = first ? ln.template nnz_pass<true>(indices, data, Y, w.k0, w.k1, a, 1.f, ln.grp, C::NG)
+                    : ln.template nnz_pass<false>(indices, data, Y, w.k0, w.k1, a, -1.f, ln.grp, C::NG);
+    ln.across_groups(acc);
+    ln.store(partials + (int64_t)w.slot * F, acc);
+  }
+}
+
+template <int F, int NV>
+__global__ void __launch_bounds__(32 * kCgWarps)
+cg_combine_kernel(float *X, int64_t row_offset, const float *__restrict__ Greg, const WorkItem *__restrict__ finish,
+                  int n_finish, float *rst, float *pst, float *scal, const float *partials, int first) {
+  using Vec = VecT<NV>;
+  __shared__ __align__(16) float xs_all[kCgWarps * F];
+  const Lane<F, NV> ln = make_lane<F, NV>(xs_all);
+  const int g = blockIdx.x * kCgWarps + (threadIdx.x >> 5);
+  if (g >= n_finish) return;
+  const WorkItem w = finish[g];  // row, first slot, number of slots
+  float *xrow = X + (row_offset + w.row) * F;
+  if (!first && scal[2 * g + 1] != 0.f) return;
+  Vec sum = ln.zero();
+  for (int s = 0; s < w.k1; ++s) {  // fixed slot order
+    const Vec part = ln.load_rw(partials + (int64_t)(w.k0 + s) * F);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) add4(sum.v[i], part.v[i]);
+  }
+  Vec x = ln.load_rw(xrow);
+  if (first) {
+    Vec r = ln.symv(Greg, x);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      r.v[i].x = sum.v[i].x - r.v[i].x; r.v[i].y = sum.v[i].y - r.v[i].y;
+      r.v[i].z = sum.v[i].z - r.v[i].z; r.v[i].w = sum.v[i].w - r.v[i].w;
+    }
+    const float rsold = ln.dot(r, r);
+    ln.store(rst + (int64_t)g * F, r);
+    ln.store(pst + (int64_t)g * F, r);
+    if (ln.lane == 0) {
+      scal[2 * g] = rsold;
+      scal[2 * g + 1] = rsold < 1e-20f ? 1.f : 0.f;
+    }
+    return;
+  }
+  Vec p = ln.load_rw(pst + (int64_t)g * F);
+  Vec r = ln.load_rw(rst + (int64_t)g * F);
+  const float rsold = scal[2 * g];
+  Vec Ap = ln.symv(Greg, p);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) add4(Ap.v[i], sum.v[i]);
+  const float alpha = rsold / ln.dot(p, Ap);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    axpy4(x.v[i], alpha, p.v[i]);
+    axpy4(r.v[i], -alpha, Ap.v[i]);
+  }
+  const float rsnew = ln.dot(r, r);
+  ln.store(xrow, x);
+  if (rsnew < 1e-20f) {
+    if (ln.lane == 0) scal[2 * g + 1] = 1.f;
+    return;
+  }
+  const float beta = rsnew / rsold;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    p.v[i].x = fmaf(beta, p.v[i].x, r.v[i].x); p.v[i].y = fmaf(beta, p.v[i].y, r.v[i].y);
+    p.v[i].z = fmaf(beta, p.v[i].z, r.v[i].z); p.v[i].w = fmaf(beta, p.v[i].w, r.v[i].w);
+  }
+  ln.store(rst + (int64_t)g * F, r);
+  ln.store(pst + (int64_t)g * F, p);
+  if (ln.lane == 0) scal[2 * g] = rsnew;
+}
+
+__global__ void zero_counters(int32_t *counters) {
   if (threadIdx.x < 16) counters[threadIdx.x] = 0;
-  if (threadIdx.x < 8) d[threadIdx.x] = 0.0;
 }
 
-template <int F>
+template <int F, int NV>
 int run_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps) {
-  zero_scalars<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->dscalars);
+  zero_counters<<<1, 32, 0, ctx->stream>>>(ctx->counters);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
   if (C->n_work) {
     const int64_t want = ceil_div(C->n_work, kCgWarps);
-    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 6);
     ProfScope prof(ctx, kProfCg);
-    cg_half_kernel<F><<<grid, 32 * kCgWarps, 0, ctx->stream>>>(C->indices, C->data, Y->d, X->d, C->row_offset, ctx->Greg,
+    cg_rows_kernel<F, NV><<<grid, 32 * kCgWarps, 0, ctx->stream>>>(C->indices, C->data, Y->d, X->d, C->row_offset, ctx->Greg,
                                                               C->work, (int)C->n_work, ctx->counters, cg_steps);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }
   if (C->n_finish) {
-    const int grid = (int)std::min<int64_t>(C->n_finish, (int64_t)ctx->sm_count * 2);
+    // scratch: partials[n_slots][F] | rst[n_finish][F] | pst[n_finish][F] | scal[n_finish][2]
+    const int64_t floats = (C->n_slots + 2 * C->n_finish) * (int64_t)F + 2 * C->n_finish;
+    int rc = ensure_scratch(ctx, floats * (int64_t)sizeof(float));
+    if (rc != ALS_OK) return rc;
+    float *partials = (float *)ctx->scratch;
+    float *rst = partials + C->n_slots * (int64_t)F;
+    float *pst = rst + C->n_finish * (int64_t)F;
+    float *scal = pst + C->n_finish * (int64_t)F;
+    const int cgrid = (int)std::min<int64_t>(ceil_div(C->n_slots, kCgWarps), (int64_t)ctx->sm_count * 6);
+    const int fgrid = (int)ceil_div(C->n_finish, kCgWarps);
     ProfScope prof(ctx, kProfCgGiant);
-    cg_giant_kernel<F><<<grid, 32 * kCgGiantWarps, 0, ctx->stream>>>(C->indptr, C->indices, C->data, Y->d, X->d,
-                                                                    C->row_offset, ctx->Greg, C->finish,
-                                                                    (int)C->n_finish, cg_steps);
-    ALS_CUDA(cudaGetLastError());
-    ctx->launches++;
+    for (int pass = 0; pass <= cg_steps; ++pass) {
+      const int first = pass == 0;
+      cg_chunk_kernel<F, NV><<<cgrid, 32 * kCgWarps, 0, ctx->stream>>>(C->indices, C->data, Y->d, X->d, C->row_offset,
+                                                                   C->chunks, C->chunk_owner, (int)C->n_slots, pst, scal,
+                                                                   partials, first);
+      ALS_CUDA(cudaGetLastError());
+      cg_combine_kernel<F, NV><<<fgrid, 32 * kCgWarps, 0, ctx->stream>>>(X->d, C->row_offset, ctx->Greg, C->finish,
+                                                                     (int)C->n_finish, rst, pst, scal, partials, first);
+      ALS_CUDA(cudaGetLastError());
+      ctx->launches += 2;
+    }
   }
-  return ALS_OK;
-}
-
-template <int F>
-int run_loss_nnz(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y) {
-  if (!C->n_work) return ALS_OK;
-  const int64_t want = ceil_div(C->n_work, 8);
-  const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
-  ProfScope prof(ctx, kProfLoss);
-  loss_nnz_kernel<F><<<grid, 256, 0, ctx->stream>>>(C->indices, C->data, Y->d, X->d, C->row_offset, C->work,
-                                                    (int)C->n_work, ctx->counters, ctx->dscalars);
-  ALS_CUDA(cudaGetLastError());
-  ctx->launches++;
   return ALS_OK;
 }
 
 }  // namespace
-
-#define ALS_DISPATCH_F(ld, CALL)                                                              \
-  switch ((ld) / 16) {                                                                        \
-    case 1: return CALL(16);                                                                  \
-    case 2: return CALL(32);                                                                  \
-    case 3: return CALL(48);                                                                  \
-    case 4: return CALL(64);                                                                  \
-    case 5: return CALL(80);                                                                  \
-    case 6: return CALL(96);                                                                  \
-    case 7: return CALL(112);                                                                 \
-    case 8: return CALL(128);                                                                 \
-    default:                                                                                  \
-      set_error("factors padded to %d > 128 are not supported yet", (ld));                    \
-      return ALS_E_UNSUPPORTED;                                                               \
-  }
 
 int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps) {
   if (X->ld != Y->ld) {
     set_error("cg: X and Y strides differ (%d vs %d)", X->ld, Y->ld);
     return ALS_E_INVALID;
   }
-#define CALL(FF) run_cg<FF>(ctx, C, X, Y, cg_steps)
-  ALS_DISPATCH_F(Y->ld, CALL)
-#undef CALL
-}
-
-static int loss_nnz_dispatch(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y) {
-#define CALL(FF) run_loss_nnz<FF>(ctx, C, X, Y)
-  ALS_DISPATCH_F(Y->ld, CALL)
-#undef CALL
-}
-
-// Requires ctx->G == Y^T Y on entry (als_calculate_loss computes it first).
-int launch_loss(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y, float reg, double *loss) {
-  if (X->ld != Y->ld) {
-    set_error("loss: X and Y strides differ (%d vs %d)", X->ld, Y->ld);
-    return ALS_E_INVALID;
+  // float4 words per lane: 1 keeps the per-row overhead (symv + cross-group reductions) lowest, which wins
+  // on short rows; ALS_B200_CG_NV overrides for experiments
+  static int nv_env = -1;
+  if (nv_env < 0) {
+    const char *e = getenv("ALS_B200_CG_NV");
+    nv_env = e ? atoi(e) : 0;
   }
-  const int ld = Y->ld;
-  // keep Y^T Y in Greg, then overwrite G with X^T X restricted to C's rows
-  ALS_CUDA(cudaMemcpyAsync(ctx->Greg, ctx->G, sizeof(float) * ld * ld, cudaMemcpyDeviceToDevice, ctx->stream));
-  als_factors Xs = *X;
-  Xs.d = X->d + C->row_offset * (int64_t)ld;
-  Xs.rows = C->rows;
-  int rc = launch_gramian(ctx, &Xs);
-  if (rc != ALS_OK) return rc;
-  zero_scalars<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->dscalars);
-  ALS_CUDA(cudaGetLastError());
-  frob_trace_kernel<<<1, 256, 0, ctx->stream>>>(ctx->Greg, ctx->G, Y->f, ld, ctx->dscalars);
-  ALS_CUDA(cudaGetLastError());
-  ctx->launches += 2;
-  rc = loss_nnz_dispatch(ctx, C, X, Y);
-  if (rc != ALS_OK) return rc;
-  double h[8];
-  ALS_CUDA(cudaMemcpyAsync(h, ctx->dscalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
-  // h[0] nnz terms, h[1] sum|c|, h[2] <YtY, XtX>, h[3] tr(YtY) = ||Y||^2, h[4] tr(XtX) = ||X_C||^2
-  // loss[0] numerator (without the division), loss[1] total confidence, so that shards can be summed
-  // by the host: loss = (sum num) / (sum conf + U*I - nnz)       (_als.pyx:307-308)
-  loss[0] = h[2] + h[0] + (double)reg * h[4];
-  loss[1] = h[1];
-  loss[2] = (double)reg * h[3];  // item-norm part: identical on every shard, add once
-  return ALS_OK;
+  const int nv = nv_env ? nv_env : 2;  // measured on B200: C2 (f=64) 6.0 ms/iter at 2 vs 6.6 (1) and 9.3 (4); C3 (f=128) 9.9 vs 11.2 and 11.9
+#define ALS_CG_CASE(FF)                                                   \
+  case FF / 16:                                                           \
+    if (nv == 4) return run_cg<FF, 4>(ctx, C, X, Y, cg_steps);            \
+    if (nv == 2) return run_cg<FF, 2>(ctx, C, X, Y, cg_steps);            \
+    return run_cg<FF, 1>(ctx, C, X, Y, cg_steps);
+  switch (Y->ld / 16) {
+    ALS_CG_CASE(16)
+    ALS_CG_CASE(32)
+    ALS_CG_CASE(48)
+    ALS_CG_CASE(64)
+    ALS_CG_CASE(80)
+    ALS_CG_CASE(96)
+    ALS_CG_CASE(112)
+    ALS_CG_CASE(128)
+    default:
+      set_error("cg: factors padded to %d > 128 are not supported yet", Y->ld);
+      return ALS_E_UNSUPPORTED;
+  }
+#undef ALS_CG_CASE
 }
 
 }  // namespace als

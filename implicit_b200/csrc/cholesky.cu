@@ -17,6 +17,7 @@
 // Giant rows are split into chunks whose partial (A, b) go to global scratch and are summed in a
 // fixed order by a second "finish" launch, so results do not depend on scheduling.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -182,7 +183,7 @@ __device__ __forceinline__ void consume_kstep(RowState<NB> &st, const float *sta
 // solution, which is how failure is detected (LAPACK posv info != 0, _als.pyx:131-138).
 template <int NB>
 __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *zb, float *dinv,
-                                             float *__restrict__ xout, int lane, bool &ok) {
+                                             float *__restrict__ xout, int lane, bool &ok, int dbg) {
   using C = Cfg<NB>;
   constexpr int F = C::F;
   const int g = lane >> 2, t = lane & 3;
@@ -221,6 +222,7 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
       }
     }
     // 3. eliminate the 8 pivots
+    if (!(dbg & 2))
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const float d = v[0][r];  // meaningful on lane r: the pivot
@@ -253,7 +255,7 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
     }
     __syncwarp();
     // 4. trailing update in registers: A[m][n] -= sum_r U[r][m] U[r][n]; b[m] -= sum_r U[r][m] z[r]
-    if (p + 1 < C::NT8) {
+    if (p + 1 < C::NT8 && !(dbg & 4)) {
       const float z0 = zb[8 * p + t], z1 = zb[8 * p + t + 4];
       uint32_t uh0[C::NT8], ul0[C::NT8], uh1[C::NT8], ul1[C::NT8];
 #pragma unroll
@@ -305,6 +307,7 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
     zz[q] = zb[mm];
     xx[q] = 0.f;
   }
+  if (!(dbg & 1))
 #pragma unroll
   for (int p = C::NT8 - 1; p >= 0; --p) {
     const int qp = (8 * p) >> 5;        // register slot of the panel's rows
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3)
 cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
                      float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
                      const WorkItem *__restrict__ work, int n_work, int32_t *counter, float *slots,
-                     long long *bad_row, int pass) {
+                     long long *bad_row, int pass, int dbg) {
   using C = Cfg<NB>;
   constexpr int F = C::F;
   extern __shared__ __align__(16) float smem[];
@@ -490,7 +493,7 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
         for (int m = lane; m < F; m += 32) xout[m] = 0.f;
       } else if (whole || finish) {
         bool ok = true;
-        factor_solve<NB>(st, U, zb, dinv, xout, lane, ok);
+        if (!(dbg & 8)) factor_solve<NB>(st, U, zb, dinv, xout, lane, ok, dbg);
         if (!ok && lane == 0) atomicMin(bad_row, (long long)(row_offset + wi.row));
         __syncwarp();
       }
@@ -510,9 +513,21 @@ __global__ void init_solver_scalars(int32_t *counters, long long *bad_row) {
   if (threadIdx.x == 0) bad_row[0] = LLONG_MAX;
 }
 
+// Timing ablations (results are WRONG when set): ALS_B200_DEBUG bit0 skip back-substitution, bit1 skip pivot
+// elimination, bit2 skip trailing updates, bit3 skip the whole factorisation.  Never set in production.
+static int debug_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("ALS_B200_DEBUG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 template <int NB>
 int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_factors *Y) {
   using C = Cfg<NB>;
+  const int dbg = debug_flags();
   const int smem = C::WARP_FLOATS * kWarpsPerCta * (int)sizeof(float);
   auto kern = cholesky_half_kernel<NB>;
   ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -537,7 +552,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
     ProfScope prof(ctx, kProfCholesky);
     kern<<<grid, 32 * kWarpsPerCta, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
                                                           Cm->work, (int)Cm->n_work, ctx->counters, slots,
-                                                          ctx->bad_row, 0);
+                                                          ctx->bad_row, 0, dbg);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -547,7 +562,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
     ProfScope prof(ctx, kProfCholFinish);
     kern<<<grid, 32 * kWarpsPerCta, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
                                                           Cm->finish, (int)Cm->n_finish, ctx->counters + 1, slots,
-                                                          ctx->bad_row, 1);
+                                                          ctx->bad_row, 1, dbg);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }

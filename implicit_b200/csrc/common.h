@@ -101,9 +101,11 @@ struct als_csr {
   // schedule
   als::WorkItem *work = nullptr;    // main pass: whole rows + chunks, longest first
   int64_t n_work = 0;
-  als::WorkItem *finish = nullptr;  // finish pass: one per giant row
+  als::WorkItem *finish = nullptr;  // finish pass: one per giant row (row, first slot, #slots)
   int64_t n_finish = 0;
   int64_t n_slots = 0;
+  als::WorkItem *chunks = nullptr;  // the n_slots chunk items in slot order (CG walks them pass by pass)
+  int32_t *chunk_owner = nullptr;   // chunk -> index of its row in `finish`
 };
 
 namespace als {

@@ -103,6 +103,9 @@ int als_factors_create(als_ctx *ctx, int64_t rows, int factors, als_factors **ou
 int als_factors_upload(als_ctx *ctx, als_factors *f, const float *host, int64_t row0, int64_t nrows);
 int als_factors_download(als_ctx *ctx, const als_factors *f, float *host, int64_t row0, int64_t nrows);
 int als_factors_shape(const als_factors *f, int64_t *rows, int *factors, int *stride);
+/* *has_nan = 1 if any element is NaN (device-side scan).  Replaces the host np.isnan pass of
+ * RecommenderBase._check_factors, implicit/recommender_base.py:218-223. */
+int als_factors_has_nan(als_ctx *ctx, const als_factors *f, int *has_nan);
 int als_factors_destroy(als_factors *f);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */
