@@ -476,8 +476,12 @@ ALS_API int als_factors_upload(als_ctx *ctx, als_factors *f, const float *host, 
   if (nrows == 0) return ALS_OK;
   ALS_CUDA(cudaSetDevice(ctx->device));
   // ordered after any kernel already queued on the compute stream that reads/writes f
-  ALS_CUDA(cudaMemcpy2DAsync(f->d + row0 * f->ld, sizeof(float) * f->ld, host, sizeof(float) * f->f,
-                             sizeof(float) * f->f, nrows, cudaMemcpyHostToDevice, ctx->stream));
+  if (f->f == f->ld) {  // no padding: one contiguous copy (a pitched copy of 256-byte rows is several times slower)
+    ALS_CUDA(cudaMemcpyAsync(f->d + row0 * f->ld, host, sizeof(float) * f->f * nrows, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    ALS_CUDA(cudaMemcpy2DAsync(f->d + row0 * f->ld, sizeof(float) * f->ld, host, sizeof(float) * f->f,
+                               sizeof(float) * f->f, nrows, cudaMemcpyHostToDevice, ctx->stream));
+  }
   ALS_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffer may be pageable and reused by the caller
   return ALS_OK;
 }
@@ -488,8 +492,12 @@ ALS_API int als_factors_download(als_ctx *ctx, const als_factors *f, float *host
               "als_factors_download: rows [%lld, %lld) out of range", (long long)row0, (long long)(row0 + nrows));
   if (nrows == 0) return ALS_OK;
   ALS_CUDA(cudaSetDevice(ctx->device));
-  ALS_CUDA(cudaMemcpy2DAsync(host, sizeof(float) * f->f, f->d + row0 * f->ld, sizeof(float) * f->ld,
-                             sizeof(float) * f->f, nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  if (f->f == f->ld) {
+    ALS_CUDA(cudaMemcpyAsync(host, f->d + row0 * f->ld, sizeof(float) * f->f * nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    ALS_CUDA(cudaMemcpy2DAsync(host, sizeof(float) * f->f, f->d + row0 * f->ld, sizeof(float) * f->ld,
+                               sizeof(float) * f->f, nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   ALS_CUDA(cudaStreamSynchronize(ctx->stream));
   return ALS_OK;
 }

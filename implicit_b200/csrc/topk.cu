@@ -22,7 +22,6 @@
 namespace als {
 namespace {
 
-constexpr int kTopkThreads = 256;
 
 template <int F, int TQ>
 struct TkCfg {
@@ -30,14 +29,18 @@ struct TkCfg {
   static constexpr int IT = (F <= 64) ? 128 : 64;  // items per tile
   static constexpr int LDF = F + 4;              // operand row stride: conflict-free mma fragment reads
   static constexpr int SLD = IT + 4;             // score tile stride
-  static constexpr int ROWS_PER_WARP = QB / 8;
+  // 16 warps for the common 64-row block: with 144 KB of shared memory only one CTA fits per SM, and 8
+  // warps (2 per scheduler) left the tensor pipe idle 2/3 of the time (profiles/r01_topk_*_v3.txt)
+  static constexpr int NW = (TQ >= 4) ? 16 : 8;
+  static constexpr int THREADS = 32 * NW;
+  static constexpr int ROWS_PER_WARP = QB / NW;
   // warp tiling of the QB x IT score tile: WY x WX warps, each MT m16-tiles x NT n8-tiles
   static constexpr int MT = QB >= 32 ? 2 : 1;
   static constexpr int WY = QB / (16 * MT);
-  static constexpr int WX = 8 / WY;
+  static constexpr int WX = NW / WY;
   static constexpr int NT = IT / (8 * WX);
-  static_assert(WY * WX == 8 && NT >= 1, "8 warps per CTA");
-  static int smem_floats(int k) { return 2 * QB * LDF + 2 * IT * LDF + QB * SLD + 2 * QB * k + 2 * QB; }
+  static_assert(WY * WX == NW && NT >= 1 && ROWS_PER_WARP >= 1, "warp tiling");
+  static int smem_floats(int k) { return 2 * QB * LDF + 2 * IT * LDF + QB * SLD + 2 * QB * k + 3 * QB; }
 };
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -95,7 +98,7 @@ __device__ __forceinline__ void list_insert(float *ls, int *lc, int &cnt, int k,
 }
 
 template <int F, int TQ>
-__global__ void __launch_bounds__(kTopkThreads, 1)
+__global__ void __launch_bounds__(TkCfg<F, TQ>::THREADS, 1)
 topk_kernel(const float *__restrict__ items, int n_items, const float *__restrict__ queries,
             const int32_t *__restrict__ query_rows, int n_query, int k, const float *__restrict__ item_norms,
             const uint8_t *__restrict__ item_mask, const int32_t *__restrict__ liked_indptr,
@@ -105,23 +108,41 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
   extern __shared__ __align__(16) float smem[];
   uint32_t *Qh = reinterpret_cast<uint32_t *>(smem);  // [QB][LDF] query block, TF32 hi part
   uint32_t *Ql = Qh + QB * LDF;                        // [QB][LDF] lo part
-  uint32_t *Ih = Ql + QB * LDF;                        // [IT][LDF] item tile, hi
-  uint32_t *Il = Ih + IT * LDF;                        // [IT][LDF] lo
-  float *Ss = reinterpret_cast<float *>(Il + IT * LDF);  // [QB][SLD]
+  float *Ib = reinterpret_cast<float *>(Ql + QB * LDF);  // [2][IT][LDF] raw item tiles (cp.async double buffer)
+  float *Ss = Ib + 2 * IT * LDF;      // [QB][SLD]
   float *Ls = Ss + QB * SLD;          // [QB][k]
   int *Lc = reinterpret_cast<int *>(Ls + QB * k);  // [QB][k]
   int *Cnt = Lc + QB * k;             // [QB]
   int *Cur = Cnt + QB;                // [QB] liked-list cursors
+  int *Nxt = Cur + QB;                // [QB] column of the next liked entry (INT_MAX when exhausted)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wy = warp % C::WY, wx = warp / C::WY;  // this warp's block of the score tile
   const float neginf = -FLT_MAX;
+  constexpr int NCH = IT / 32;
+  const int n_tiles = (n_items + IT - 1) / IT;
+
+  // item tile `tile` -> buffer: 16-byte cp.async, rows past n_items zero-filled (src-size 0)
+  auto issue_tile = [&](int tile) {
+    float *dst = Ib + (tile & 1) * IT * LDF;
+    const int i0 = tile * IT;
+    for (int e = tid; e < IT * (F / 4); e += C::THREADS) {
+      const int it = e / (F / 4), fc = e % (F / 4);
+      const bool in = i0 + it < n_items;
+      const float *src = items + (int64_t)(in ? i0 + it : 0) * F + 4 * fc;
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + it * LDF + 4 * fc);
+      const int nbytes = in ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
 
   for (int q0 = blockIdx.x * QB; q0 < n_query; q0 += gridDim.x * QB) {
     __syncthreads();
+    issue_tile(0);
     // stage the query block, split into TF32 hi / lo once; rows past n_query are zero
-    for (int e = tid; e < QB * (F / 4); e += kTopkThreads) {
+    for (int e = tid; e < QB * (F / 4); e += C::THREADS) {
       const int q = e / (F / 4), fc = e % (F / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (q0 + q < n_query) {
@@ -133,23 +154,25 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
       *reinterpret_cast<uint4 *>(Qh + q * LDF + 4 * fc) = hi;
       *reinterpret_cast<uint4 *>(Ql + q * LDF + 4 * fc) = lo;
     }
-    for (int q = tid; q < QB; q += kTopkThreads) {
+    for (int q = tid; q < QB; q += C::THREADS) {
       Cnt[q] = 0;
-      Cur[q] = (liked_indptr && q0 + q < n_query) ? liked_indptr[q0 + q] : 0;
+      int cur = 0, nxt = INT_MAX;
+      if (liked_indptr && q0 + q < n_query) {
+        cur = liked_indptr[q0 + q];
+        if (cur < liked_indptr[q0 + q + 1]) nxt = liked_indices[cur];
+      }
+      Cur[q] = cur;
+      Nxt[q] = nxt;
     }
 
-    for (int i0 = 0; i0 < n_items; i0 += IT) {
-      __syncthreads();  // previous tile fully consumed
-      for (int e = tid; e < IT * (F / 4); e += kTopkThreads) {
-        const int it = e / (F / 4), fc = e % (F / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i0 + it < n_items) v = __ldg(reinterpret_cast<const float4 *>(items + (int64_t)(i0 + it) * F) + fc);
-        uint4 hi, lo;
-        split4(v, hi, lo);
-        *reinterpret_cast<uint4 *>(Ih + it * LDF + 4 * fc) = hi;
-        *reinterpret_cast<uint4 *>(Il + it * LDF + 4 * fc) = lo;
-      }
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const int i0 = tile * IT;
+      // the buffer the next tile lands in was last read two iterations ago (a barrier has passed since)
+      if (tile + 1 < n_tiles) issue_tile(tile + 1);
+      else asm volatile("cp.async.commit_group;\n" ::: "memory");
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
       __syncthreads();
+      const float *It = Ib + (tile & 1) * IT * LDF;
       // ---- scores on the tensor cores: 3xTF32 (lo*hi + hi*lo + hi*hi), fp32 accumulate.
       // Warp (wy, wx) owns queries [16 MT wy, +16 MT) x items [8 NT wx, +8 NT) of the tile.
       float acc[MT][NT][4];
@@ -168,10 +191,13 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
           al[m][0] = Ql[r0]; al[m][1] = Ql[r1]; al[m][2] = Ql[r0 + 4]; al[m][3] = Ql[r1 + 4];
         }
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
+        for (int n = 0; n < NT; ++n) {  // item operand split on the fly (the tile is staged raw by cp.async)
           const int c0 = (ib + 8 * n + g) * LDF + 8 * kk + t;
-          bh[n][0] = Ih[c0]; bh[n][1] = Ih[c0 + 4];
-          bl[n][0] = Il[c0]; bl[n][1] = Il[c0 + 4];
+          const float v0 = It[c0], v1 = It[c0 + 4];
+          bh[n][0] = (__float_as_uint(v0) + 0x1000u) & 0xffffe000u;
+          bh[n][1] = (__float_as_uint(v1) + 0x1000u) & 0xffffe000u;
+          bl[n][0] = __float_as_uint(v0 - __uint_as_float(bh[n][0]));
+          bl[n][1] = __float_as_uint(v1 - __uint_as_float(bh[n][1]));
         }
 #pragma unroll
         for (int term = 0; term < 3; ++term)  // term-major: a tile's three MMAs chain through its accumulator
@@ -214,7 +240,7 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
         const int row = warp * C::ROWS_PER_WARP + rr;
         if (q0 + row >= n_query) break;
         float *srow = Ss + row * SLD;
-        if (liked_indptr) {  // topk.pyx:51-53 (row indices sorted ascending by the host)
+        if (liked_indptr && Nxt[row] < i0 + IT) {  // topk.pyx:51-53 (row indices sorted ascending by the host)
           const int end = liked_indptr[q0 + row + 1];
           int cur = Cur[row];
           for (;;) {
@@ -227,30 +253,47 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
             if (n < 32) break;
           }
           __syncwarp();
-          if (lane == 0) Cur[row] = cur;
+          if (lane == 0) {
+            Cur[row] = cur;
+            Nxt[row] = cur < end ? liked_indices[cur] : INT_MAX;
+          }
         }
         float *ls = Ls + row * k;
         int *lc = Lc + row * k;
         int cnt = Cnt[row];
         float thr = (cnt == k) ? ls[0] : neginf;
-        for (int c0 = 0; c0 < IT; c0 += 32) {
-          const int col = i0 + c0 + lane;
-          const float s = srow[c0 + lane];
-          unsigned m = __ballot_sync(0xffffffffu, col < n_items && (cnt < k || s > thr));
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const float cs = __shfl_sync(0xffffffffu, s, b);
-            if (cnt < k || cs > thr) {  // select.h:23, re-checked against the updated threshold
-              list_insert(ls, lc, cnt, k, cs, i0 + c0 + b, lane);
-              thr = (cnt == k) ? ls[0] : neginf;
+        // fast path: test the whole row of the tile against the threshold first (hits are rare once
+        // the k-list has warmed up); the masks stay valid supersets because the threshold only rises
+        float sv[NCH];
+        unsigned mk[NCH];
+        unsigned any = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) sv[c] = srow[32 * c + lane];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          mk[c] = __ballot_sync(0xffffffffu, (i0 + 32 * c + lane) < n_items && (cnt < k || sv[c] > thr));
+          any |= mk[c];
+        }
+        if (any) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            unsigned m = mk[c];
+            while (m) {  // column order inside the chunk: exact select.h semantics
+              const int b = __ffs(m) - 1;
+              m &= m - 1;
+              const float cs = __shfl_sync(0xffffffffu, sv[c], b);
+              if (cnt < k || cs > thr) {  // select.h:23, re-checked against the updated threshold
+                list_insert(ls, lc, cnt, k, cs, i0 + 32 * c + b, lane);
+                thr = (cnt == k) ? ls[0] : neginf;
+              }
             }
           }
+          if (lane == 0) Cnt[row] = cnt;
+          __syncwarp();
         }
-        if (lane == 0) Cnt[row] = cnt;
-        __syncwarp();
       }
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     // ---- emit: descending by (score, col) (select.h:33); the tail past cnt stays zero (topk.pyx:20-21)
     __syncthreads();
     for (int rr = 0; rr < C::ROWS_PER_WARP; ++rr) {
@@ -302,7 +345,7 @@ int run_topk(als_ctx *ctx, const TopkArgs &a) {
   const int64_t blocks = ceil_div(a.n_query, C::QB);
   const int grid = (int)std::min<int64_t>(blocks, (int64_t)ctx->sm_count * 2);
   ProfScope prof(ctx, kProfTopk);
-  kern<<<grid, kTopkThreads, smem, ctx->stream>>>(a.items, a.n_items, a.queries, a.query_rows, a.n_query, a.k, a.norms,
+  kern<<<grid, C::THREADS, smem, ctx->stream>>>(a.items, a.n_items, a.queries, a.query_rows, a.n_query, a.k, a.norms,
                                                   a.mask, a.liked_indptr, a.liked_indices, a.ids, a.scores);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
