@@ -87,7 +87,10 @@ def load(build=True):
     global _lib
     if _lib is None:
         path = _build.LIB
-        if build and os.environ.get("ALS_B200_NO_BUILD") != "1":
+        override = os.environ.get("ALS_B200_LIB")  # A/B timing of kernel variants (tools/ablate.py)
+        if override:
+            path = override
+        elif build and os.environ.get("ALS_B200_NO_BUILD") != "1":
             path = _build.build()
         if not os.path.exists(path):
             raise ImportError(f"{path} is missing: run `python -m implicit_b200._build` (needs nvcc)")

@@ -10,10 +10,11 @@
 //            (hi*hi + hi*lo + lo*hi) so the result is fp32-faithful (plain TF32 would miss the 1e-4
 //            parity bar); b_u = sum_{c_k > 0} c_k y_k rides along in fp32 FMAs;
 //   solve    a right-looking blocked Cholesky with 8-row panels: each panel is spilled to shared
-//            memory, factored (8x8 diagonal block redundantly per lane, panel columns one per lane),
-//            and the trailing matrix is updated IN REGISTERS by the same 3xTF32 mma tiles; the
-//            forward substitution rides along as one more column, the back substitution runs on the
-//            packed U left in shared memory.
+//            memory, one lane owns one panel column (the rhs slice and 8 unit vectors ride along as
+//            extra columns), the 8 pivots are eliminated LDL^T-style with warp shuffles and the rows
+//            scaled by 1/sqrt(d) afterwards; the trailing matrix is updated IN REGISTERS by the same
+//            3xTF32 mma tiles; the back substitution resolves a panel at a time with the inverse of
+//            its diagonal block (the forward-substituted unit vectors) on the packed U in shared memory.
 // Giant rows are split into chunks whose partial (A, b) go to global scratch and are summed in a
 // fixed order by a second "finish" launch, so results do not depend on scheduling.
 #include <limits.h>
@@ -57,6 +58,17 @@ __device__ __forceinline__ uint32_t rn_tf32(float x) { return (__float_as_uint(x
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
   hi = rn_tf32(x);
   lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 template <int NB>
@@ -194,8 +206,8 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
     float *Up = U + C::poff(p);
     const int sp = C::pstride(p);
     const int Wp = F - 8 * p;
-    constexpr int NJmax = (F + 1 + 31) / 32;
-    const int NJ = (Wp + 1 + 31) / 32;
+    constexpr int NJmax = (F + 9 + 31) / 32;
+    const int NJ = (Wp + 9 + 31) / 32;
     // 1. spill panel rows 8p..8p+7 (columns 8p..F-1) and the matching slice of b
 #pragma unroll
     for (int j = p; j < C::NT8; ++j) {
@@ -209,7 +221,9 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
       if (t == 0) zb[8 * p + g] = bq;
     }
     __syncwarp();
-    // 2. one panel column per lane (local column Wp is the rhs slice)
+    // 2. one panel column per lane.  Local columns [0, Wp) are the matrix (the first 8 = the diagonal block),
+    //    Wp is the rhs slice, and Wp+1 .. Wp+8 are the unit vectors e_0..e_7: forward-substituted with the rest
+    //    they become the rows of U_d^-1, which lets the back substitution resolve a whole panel at once.
     float v[NJmax][8];
 #pragma unroll
     for (int j = 0; j < NJmax; ++j) {
@@ -217,39 +231,55 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
         const int c = lane + 32 * j;
         const float *colp = (c < Wp) ? (Up + c) : (zb + 8 * p);
         const int rs = (c < Wp) ? sp : 1;
+        const int e = c - Wp - 1;  // unit-vector index for the identity columns
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[j][r] = (c <= Wp) ? colp[r * rs] : 0.f;
+        for (int r = 0; r < 8; ++r) v[j][r] = (c <= Wp) ? colp[r * rs] : (e == r ? 1.f : 0.f);
       }
     }
-    // 3. eliminate the 8 pivots
-    if (!(dbg & 2))
+    // 3. eliminate the 8 pivots, LDL^T style: the only serial chain is  1/d_r -> (one shuffle) -> the next
+    //    pivot's own update; the scaling by 1/sqrt(d_r) that turns the rows into U is applied afterwards,
+    //    for all 8 rows at once.  u = a[r][r2] / d_r comes from the lane that owns diagonal-block column r2.
+    if (!(dbg & 2)) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float d = v[0][r];  // meaningful on lane r: the pivot
-      float s = rsqrtf(d);
-      s = s * fmaf(-0.5f * d * s, s, 1.5f);  // one Newton step: full fp32 accuracy
-      const float inv = __shfl_sync(0xffffffffu, s, r);
+      for (int r = 0; r < 8; ++r) {
+        const float d = v[0][r];  // meaningful on lane r: the pivot
+        float rc = rcp_approx(d);
+        rc = rc * fmaf(-d, rc, 2.f);  // Newton step
+        const float rinv = __shfl_sync(0xffffffffu, rc, r);
 #pragma unroll
-      for (int j = 0; j < NJmax; ++j)
-        if (j < NJ) v[j][r] *= inv;
-      if (lane == r) dinv[8 * p + r] = inv;
+        for (int r2 = r + 1; r2 < 8; ++r2) {
+          const float u = __shfl_sync(0xffffffffu, v[0][r], r2) * rinv;
 #pragma unroll
-      for (int r2 = r + 1; r2 < 8; ++r2) {
-        const float u = __shfl_sync(0xffffffffu, v[0][r], r2);  // U[r][8p + r2]
+          for (int j = 0; j < NJmax; ++j)
+            if (j < NJ) v[j][r2] = fmaf(-u, v[j][r], v[j][r2]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float d = __shfl_sync(0xffffffffu, v[0][r], r);
+        float s = rsqrt_approx(d);
+        s = s * fmaf(-0.5f * d * s, s, 1.5f);  // Newton step: full fp32 accuracy
 #pragma unroll
         for (int j = 0; j < NJmax; ++j)
-          if (j < NJ) v[j][r2] = fmaf(-u, v[j][r], v[j][r2]);
+          if (j < NJ) v[j][r] *= s;
       }
     }
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < NJmax; ++j) {
       if (j < NJ) {
         const int c = lane + 32 * j;
-        float *colp = (c < Wp) ? (Up + c) : (zb + 8 * p);
-        const int rs = (c < Wp) ? sp : 1;
-        if (c <= Wp) {
+        if (c >= 8 && c < Wp) {
 #pragma unroll
-          for (int r = 0; r < 8; ++r) colp[r * rs] = v[j][r];
+          for (int r = 0; r < 8; ++r) Up[r * sp + c] = v[j][r];
+        } else if (c == Wp) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) zb[8 * p + r] = v[j][r];
+        } else if (c > Wp && c <= Wp + 8) {
+          // row (c - Wp - 1) of U_d^-1 replaces that row of the diagonal block (U_d itself is not needed again)
+          float *dst = Up + (c - Wp - 1) * sp;
+          *reinterpret_cast<float4 *>(dst) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+          *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
         }
       }
     }
@@ -312,23 +342,21 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
   for (int p = C::NT8 - 1; p >= 0; --p) {
     const int qp = (8 * p) >> 5;        // register slot of the panel's rows
     const int l0 = (8 * p) & 31;        // their first lane
-    const float4 ia = *reinterpret_cast<const float4 *>(dinv + 8 * p);
-    const float4 ib4 = *reinterpret_cast<const float4 *>(dinv + 8 * p + 4);
-    const float inv[8] = {ia.x, ia.y, ia.z, ia.w, ib4.x, ib4.y, ib4.z, ib4.w};
-    // this lane's row of the diagonal block (meaningful on lanes l0..l0+7 of slot qp)
+    // this lane's row of U_d^-1 (meaningful on lanes l0..l0+7 of slot qp)
     const float4 da = *reinterpret_cast<const float4 *>(U + rowoff[qp] + 8 * p);
     const float4 db = *reinterpret_cast<const float4 *>(U + rowoff[qp] + 8 * p + 4);
-    const float ud[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+    float rhs[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) rhs[c] = __shfl_sync(0xffffffffu, zz[qp], l0 + c);
+    // x_r = sum_{c >= r} U_d^-1[r][c] rhs[c]  (entries below the diagonal of the stored rows are exactly 0)
+    const float xm = fmaf(da.x, rhs[0], fmaf(da.y, rhs[1], fmaf(da.z, rhs[2], da.w * rhs[3]))) +
+                     fmaf(db.x, rhs[4], fmaf(db.y, rhs[5], fmaf(db.z, rhs[6], db.w * rhs[7])));
     const bool in_panel = (lane >= l0) && (lane < l0 + 8);
+    if (in_panel) xx[qp] = xm;
     float xs[8];
 #pragma unroll
-    for (int r = 7; r >= 0; --r) {
-      const float xr = __shfl_sync(0xffffffffu, zz[qp], l0 + r) * inv[r];
-      xs[r] = xr;
-      if (lane == l0 + r) xx[qp] = xr;
-      if (in_panel && lane < l0 + r) zz[qp] = fmaf(-ud[r], xr, zz[qp]);  // rows above r inside the panel
-    }
-    // rows before the panel
+    for (int c = 0; c < 8; ++c) xs[c] = __shfl_sync(0xffffffffu, xm, l0 + c);
+    // rows before the panel fold it in
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       if (32 * q < 8 * p) {
@@ -336,10 +364,9 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
         if (m < 8 * p) {
           const float4 ua = *reinterpret_cast<const float4 *>(U + rowoff[q] + 8 * p);
           const float4 ub = *reinterpret_cast<const float4 *>(U + rowoff[q] + 8 * p + 4);
-          float a = zz[q];
-          a = fmaf(-ua.x, xs[0], a); a = fmaf(-ua.y, xs[1], a); a = fmaf(-ua.z, xs[2], a); a = fmaf(-ua.w, xs[3], a);
-          a = fmaf(-ub.x, xs[4], a); a = fmaf(-ub.y, xs[5], a); a = fmaf(-ub.z, xs[6], a); a = fmaf(-ub.w, xs[7], a);
-          zz[q] = a;
+          const float s0 = fmaf(ua.x, xs[0], fmaf(ua.y, xs[1], fmaf(ua.z, xs[2], ua.w * xs[3])));
+          const float s1 = fmaf(ub.x, xs[4], fmaf(ub.y, xs[5], fmaf(ub.z, xs[6], ub.w * xs[7])));
+          zz[q] -= s0 + s1;
         }
       }
     }

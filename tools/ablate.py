@@ -21,7 +21,11 @@ for it in range(3):
     p = ctx.profile_read()
 print("DEBUG=%%s cholesky ms/2 launches: %%.3f" %% (os.environ.get("ALS_B200_DEBUG","0"), p["cholesky"][0]))
 ''' % ROOT
-for flags in (0, 1, 2, 4, 6, 7, 8):
+variants = [v for v in sys.argv[1:]] or [""]
+for lib, flags in [(v, f) for v in variants for f in ((0, 1, 2, 4) if len(variants) <= 2 else (0,))]:
     env = dict(os.environ, ALS_B200_DEBUG=str(flags))
+    if lib:
+        env["ALS_B200_LIB"] = os.path.join(ROOT, lib)
+        print(lib, end=" ")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     print((r.stdout.strip().splitlines() or ["?"])[-1], r.stderr.strip()[-200:] if r.returncode else "", flush=True)
