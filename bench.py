@@ -209,7 +209,8 @@ def workload_config(cfg, args, world):
     return {"workload": f"{args.config}: synthetic power-law CSR {cfg['users']}x{cfg['items']}, {cfg['nnz']} nnz, "
                         f"factors={cfg['factors']}, {'CG(3)' if cfg['use_cg'] else 'Cholesky'}, lambda=0.01, seed={cfg['seed']}",
             "scale": args.scale, "l2": "inputs_exceed_l2 (CSR + factors > 126 MB)" if cfg["nnz"] * 8 > 126e6 else "l2_flush",
-            "parallelism": f"row-sharded dp{world}" if world > 1 else "single GPU",
+            "parallelism": (f"row-sharded dp{world}, solved rows mirrored to peer replicas over NVLink by the solve kernel"
+                            if world > 1 else "single GPU"),
             "e2e_step": f"fit(host CSR) x {E2E_ITERS} iterations + factors read back"}
 
 
@@ -231,11 +232,16 @@ def run_ours(args):
     Ciu = Cui.transpose()
     X, Y = _lib.DeviceFactors.from_host(ctx, X0), _lib.DeviceFactors.from_host(ctx, Y0)
     Cui_s, Ciu_s, usplit, isplit = Cui, Ciu, None, None
+    p2p = world > 1 and os.environ.get("ALS_B200_NO_P2P") != "1"
     if world > 1:
-        usplit = nnz_balanced_splits(Cui_host.indptr, world)
-        isplit = nnz_balanced_splits(Ciu.indptr_host(), world)
+        row_cost = 20 if use_cg else 60
+        usplit = nnz_balanced_splits(Cui_host.indptr, world, row_cost)
+        isplit = nnz_balanced_splits(Ciu.indptr_host(), world, row_cost)
         Cui_s = Cui.slice_rows(usplit[rank], usplit[rank + 1])
         Ciu_s = Ciu.slice_rows(isplit[rank], isplit[rank + 1])
+        if p2p:  # fused exchange: solved rows are stored into the peers' replicas by the solve kernel itself
+            ctx.attach_peers(X)
+            ctx.attach_peers(Y)
 
     def half(C, A, B, split):
         if use_cg:
@@ -243,7 +249,11 @@ def run_ours(args):
         else:
             _lib.least_squares(ctx, C, A, B, reg)
         if split is not None:
-            ctx.allgather_rows(A, split)
+            if p2p:
+                ctx.sync()
+                ctx.barrier()
+            else:
+                ctx.allgather_rows(A, split)
 
     def iteration():
         half(Cui_s, X, Y, usplit)

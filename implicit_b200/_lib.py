@@ -66,6 +66,10 @@ SIGNATURES = {
     "als_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "als_comm_destroy": (c_int, [c_void_p]),
     "als_comm_allgather_rows": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "als_factors_ipc_export": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "als_factors_ipc_attach": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "als_factors_ipc_detach": (c_int, [c_void_p, c_void_p]),
+    "als_comm_allgather_bytes": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "als_comm_allreduce_f64": (c_int, [c_void_p, P(c_f64), c_int, c_int]),
     "als_comm_barrier": (c_int, [c_void_p]),
 }
@@ -192,6 +196,24 @@ class Context:
     def allgather_rows(self, factors, row_splits):
         splits = np.ascontiguousarray(row_splits, dtype=np.int64)
         check(self.lib.als_comm_allgather_rows(self.h, factors.h, ptr(splits)))
+
+    def allgather_bytes(self, payload):
+        """Every rank contributes len(payload) <= 256 bytes; returns the concatenation in rank order."""
+        send = np.frombuffer(bytes(payload), dtype=np.uint8).copy()
+        recv = np.zeros(len(send) * self.world, dtype=np.uint8)
+        check(self.lib.als_comm_allgather_bytes(self.h, ptr(send), ptr(recv), len(send)))
+        return recv.tobytes()
+
+    def attach_peers(self, factors):
+        """Map the other ranks' replicas of `factors` (CUDA IPC over NVLink): from now on every solve that
+        writes it mirrors its rows into them, which replaces the all-gather after a half-iteration."""
+        h = np.zeros(64, dtype=np.uint8)
+        check(self.lib.als_factors_ipc_export(self.h, factors.h, ptr(h)))
+        allh = np.frombuffer(self.allgather_bytes(h.tobytes()), dtype=np.uint8).copy()
+        check(self.lib.als_factors_ipc_attach(self.h, factors.h, self.rank, self.world, ptr(allh)))
+
+    def detach_peers(self, factors):
+        check(self.lib.als_factors_ipc_detach(self.h, factors.h))
 
     def allreduce(self, values, op="sum"):
         v = np.ascontiguousarray(values, dtype=np.float64).copy()

@@ -8,6 +8,7 @@ reference exposes.  All arithmetic runs in libals_b200.so (hand-written sm_100a 
 this file only orders the calls the way the reference does and keeps its error behaviour.
 """
 import logging
+import os
 import time
 
 import numpy as np
@@ -64,6 +65,7 @@ class AlternatingLeastSquares:
         self.process_group = process_group
         self._device = device
         self._ctx = None
+        self._p2p = False
 
         # host copies (authoritative between calls) and device replicas
         self._user_factors = None
@@ -163,9 +165,18 @@ class AlternatingLeastSquares:
         # row shards for the multi-GPU fit (whole matrix on one GPU)
         pg = self.process_group
         Cui_s, Ciu_s, usplit, isplit = Cui, Ciu, None, None
+        self._p2p = False
         if pg is not None and pg.world > 1:
-            usplit = nnz_balanced_splits(Cui_host.indptr, pg.world)
-            isplit = nnz_balanced_splits(Ciu.indptr_host(), pg.world)
+            # shards balanced by estimated cost: a row costs its nonzeros plus a fixed factorisation /
+            # CG-recurrence term worth ~60 (Cholesky) or ~20 (CG) nonzeros (profiles/r01_cholesky_ablation*.txt)
+            row_cost = 20 if self.use_cg else 60
+            usplit = nnz_balanced_splits(Cui_host.indptr, pg.world, row_cost)
+            isplit = nnz_balanced_splits(Ciu.indptr_host(), pg.world, row_cost)
+            if os.environ.get("ALS_B200_NO_P2P") != "1":
+                # fused exchange: solved rows are stored straight into the peers' replicas over NVLink
+                ctx.attach_peers(X)
+                ctx.attach_peers(Y)
+                self._p2p = True
             Cui_s = Cui.slice_rows(usplit[pg.rank], usplit[pg.rank + 1])
             Ciu_s = Ciu.slice_rows(isplit[pg.rank], isplit[pg.rank + 1])
 
@@ -202,6 +213,10 @@ class AlternatingLeastSquares:
                 progress.close()
         if self.calculate_training_loss and loss is not None:
             log.info("Final training loss %.4f", loss)
+        if self._p2p:
+            ctx.barrier()
+            ctx.detach_peers(X)
+            ctx.detach_peers(Y)
         self._mark_device_updated("user")
         self._mark_device_updated("item")
         for c in (Cui_s, Ciu_s):
@@ -219,7 +234,11 @@ class AlternatingLeastSquares:
         else:
             _lib.least_squares(ctx, C, X, Y, self.regularization)
         if splits is not None:
-            ctx.allgather_rows(X, splits)
+            if self._p2p:
+                ctx.sync()     # my rows are in every replica ...
+                ctx.barrier()  # ... and so are everybody else's
+            else:
+                ctx.allgather_rows(X, splits)
 
     def _loss(self, C, X, Y, users, items, nnz):
         ctx = self.ctx

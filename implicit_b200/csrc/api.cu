@@ -523,8 +523,57 @@ ALS_API int als_factors_shape(const als_factors *f, int64_t *rows, int *factors,
   return ALS_OK;
 }
 
+ALS_API int als_factors_ipc_export(als_ctx *ctx, const als_factors *f, void *handle) {
+  ALS_REQUIRE(ctx && f && handle, "als_factors_ipc_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ALS_IPC_HANDLE_BYTES, "IPC handle size");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  ALS_CUDA(cudaIpcGetMemHandle(&h, f->d));
+  memcpy(handle, &h, sizeof(h));
+  return ALS_OK;
+}
+
+ALS_API int als_factors_ipc_detach(als_ctx *ctx, als_factors *f) {
+  ALS_REQUIRE(ctx && f, "als_factors_ipc_detach: NULL argument");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (void *m : f->peer_maps) cudaIpcCloseMemHandle(m);
+  f->peer_maps.clear();
+  if (f->peers_dev) cudaFree(f->peers_dev);
+  f->peers_dev = nullptr;
+  f->n_peers = 0;
+  return ALS_OK;
+}
+
+ALS_API int als_factors_ipc_attach(als_ctx *ctx, als_factors *f, int rank, int world, const void *handles) {
+  ALS_REQUIRE(ctx && f && handles, "als_factors_ipc_attach: NULL argument");
+  ALS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "als_factors_ipc_attach: bad rank %d / world %d", rank, world);
+  int rc = als_factors_ipc_detach(ctx, f);
+  if (rc != ALS_OK) return rc;
+  if (world == 1) return ALS_OK;
+  std::vector<float *> ptrs;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)r * ALS_IPC_HANDLE_BYTES, sizeof(h));
+    void *m = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      als_factors_ipc_detach(ctx, f);
+      return cuda_fail(e, "cudaIpcOpenMemHandle (peer replica)", __FILE__, __LINE__);
+    }
+    f->peer_maps.push_back(m);
+    ptrs.push_back((float *)m);
+  }
+  ALS_CUDA(cudaMalloc(&f->peers_dev, sizeof(float *) * ptrs.size()));
+  ALS_CUDA(cudaMemcpy(f->peers_dev, ptrs.data(), sizeof(float *) * ptrs.size(), cudaMemcpyHostToDevice));
+  f->n_peers = (int)ptrs.size();
+  return ALS_OK;
+}
+
 ALS_API int als_factors_destroy(als_factors *f) {
   if (!f) return ALS_OK;
+  if (f->ctx && (f->n_peers || !f->peer_maps.empty())) als_factors_ipc_detach(f->ctx, f);
   if (f->ctx) {
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);

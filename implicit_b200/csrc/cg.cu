@@ -86,6 +86,11 @@ struct Lane {
         if (ok(i)) reinterpret_cast<float4 *>(row)[sub + C::L * i] = a.v[i];
     }
   }
+  // a solved factor row: local replica + NVLink stores into the peer replicas (multi-GPU)
+  __device__ __forceinline__ void store_x(float *X, int64_t off, const Vec &a, float *const *peers, int n_peers) const {
+    store(X + off, a);
+    for (int pi = 0; pi < n_peers; ++pi) store(peers[pi] + off, a);
+  }
   // sum over the L lanes of a group (every lane of the group gets the same bits)
   __device__ __forceinline__ float gsum(float v) const {
 #pragma unroll
@@ -174,7 +179,8 @@ template <int F, int NV>
 __global__ void __launch_bounds__(32 * kCgWarps)
 cg_rows_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
                float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
-               const WorkItem *__restrict__ work, int n_work, int32_t *counter, int cg_steps) {
+               const WorkItem *__restrict__ work, int n_work, int32_t *counter, int cg_steps,
+               float *const *peers, int n_peers) {
   using C = CgCfg<F, NV>;
   using Vec = VecT<NV>;
   __shared__ __align__(16) float xs_all[kCgWarps * F];
@@ -186,10 +192,11 @@ cg_rows_kernel(const int32_t *__restrict__ indices, const float *__restrict__ da
     if (it >= n_work) break;
     const int4 w = __ldg(reinterpret_cast<const int4 *>(work) + it);
     if (w.w != -1) continue;  // chunks of giant rows: handled by the chunk / combine kernels
-    float *xrow = X + (row_offset + w.x) * F;
+    const int64_t xoff = (row_offset + w.x) * F;
+    float *xrow = X + xoff;
     const int k0 = w.y, k1 = w.z;
     if (k0 == k1) {  // no observations: zero the row (_als.pyx:182-184)
-      ln.store(xrow, ln.zero());
+      ln.store_x(X, xoff, ln.zero(), peers, n_peers);
       continue;
     }
     Vec x = ln.load_rw(xrow);  // warm start (:179)
@@ -232,7 +239,7 @@ cg_rows_kernel(const int32_t *__restrict__ indices, const float *__restrict__ da
       }
       rsold = rsnew;
     }
-    ln.store(xrow, x);
+    ln.store_x(X, xoff, x, peers, n_peers);
   }
 }
 
@@ -265,14 +272,16 @@ cg_chunk_kernel(const int32_t *__restrict__ indices, const float *__restrict__ d
 template <int F, int NV>
 __global__ void __launch_bounds__(32 * kCgWarps)
 cg_combine_kernel(float *X, int64_t row_offset, const float *__restrict__ Greg, const WorkItem *__restrict__ finish,
-                  int n_finish, float *rst, float *pst, float *scal, const float *partials, int first) {
+                  int n_finish, float *rst, float *pst, float *scal, const float *partials, int first,
+                  float *const *peers, int n_peers) {
   using Vec = VecT<NV>;
   __shared__ __align__(16) float xs_all[kCgWarps * F];
   const Lane<F, NV> ln = make_lane<F, NV>(xs_all);
   const int g = blockIdx.x * kCgWarps + (threadIdx.x >> 5);
   if (g >= n_finish) return;
   const WorkItem w = finish[g];  // row, first slot, number of slots
-  float *xrow = X + (row_offset + w.row) * F;
+  const int64_t xoff = (row_offset + w.row) * F;
+  float *xrow = X + xoff;
   if (!first && scal[2 * g + 1] != 0.f) return;
   Vec sum = ln.zero();
   for (int s = 0; s < w.k1; ++s) {  // fixed slot order
@@ -310,7 +319,7 @@ cg_combine_kernel(float *X, int64_t row_offset, const float *__restrict__ Greg, 
     axpy4(r.v[i], -alpha, Ap.v[i]);
   }
   const float rsnew = ln.dot(r, r);
-  ln.store(xrow, x);
+  ln.store_x(X, xoff, x, peers, n_peers);
   if (rsnew < 1e-20f) {
     if (ln.lane == 0) scal[2 * g + 1] = 1.f;
     return;
@@ -340,7 +349,8 @@ int run_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
     const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 6);
     ProfScope prof(ctx, kProfCg);
     cg_rows_kernel<F, NV><<<grid, 32 * kCgWarps, 0, ctx->stream>>>(C->indices, C->data, Y->d, X->d, C->row_offset, ctx->Greg,
-                                                              C->work, (int)C->n_work, ctx->counters, cg_steps);
+                                                              C->work, (int)C->n_work, ctx->counters, cg_steps, X->peers_dev,
+                                                              X->n_peers);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -363,7 +373,8 @@ int run_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
                                                                    partials, first);
       ALS_CUDA(cudaGetLastError());
       cg_combine_kernel<F, NV><<<fgrid, 32 * kCgWarps, 0, ctx->stream>>>(X->d, C->row_offset, ctx->Greg, C->finish,
-                                                                     (int)C->n_finish, rst, pst, scal, partials, first);
+                                                                     (int)C->n_finish, rst, pst, scal, partials, first,
+                                                                     X->peers_dev, X->n_peers);
       ALS_CUDA(cudaGetLastError());
       ctx->launches += 2;
     }

@@ -87,7 +87,7 @@ struct Cfg {
     return o;
   }
   static constexpr int U_FLOATS = poff(NT8);
-  static constexpr int WARP_FLOATS = NSTAGE * STAGE_FLOATS + U_FLOATS + F /* z */ + F /* 1/pivot */;
+  static constexpr int WARP_FLOATS = NSTAGE * STAGE_FLOATS + U_FLOATS + F /* z */;
   // index of tile (i, j), j >= 2i, in the upper-triangular tile list
   __host__ __device__ static constexpr int tidx(int i, int j) { return i * NT8 - i * (i - 1) + (j - 2 * i); }
   static constexpr int SLOT_FLOATS = 32 * (NTILES * 4 + NT8);
@@ -194,8 +194,9 @@ __device__ __forceinline__ void consume_kstep(RowState<NB> &st, const float *sta
 // then updated in registers with 3xTF32 mma tiles.  A non-positive pivot yields a non-finite
 // solution, which is how failure is detected (LAPACK posv info != 0, _als.pyx:131-138).
 template <int NB>
-__device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *zb, float *dinv,
-                                             float *__restrict__ xout, int lane, bool &ok, int dbg) {
+__device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *zb,
+                                             float *__restrict__ xout, int lane, bool &ok, int dbg,
+                                             float *const *peers, int n_peers, int64_t xoff) {
   using C = Cfg<NB>;
   constexpr int F = C::F;
   const int g = lane >> 2, t = lane & 3;
@@ -384,7 +385,10 @@ __device__ __forceinline__ void factor_solve(RowState<NB> &st, float *U, float *
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       const int m = lane + 32 * q;
-      if (m < F) xout[m] = xx[q];
+      if (m < F) {
+        xout[m] = xx[q];
+        for (int pi = 0; pi < n_peers; ++pi) peers[pi][xoff + m] = xx[q];  // NVLink stores into the peer replicas
+      }
     }
   }
 }
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3)
 cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
                      float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
                      const WorkItem *__restrict__ work, int n_work, int32_t *counter, float *slots,
-                     long long *bad_row, int pass, int dbg) {
+                     long long *bad_row, int pass, int dbg, float *const *peers, int n_peers) {
   using C = Cfg<NB>;
   constexpr int F = C::F;
   extern __shared__ __align__(16) float smem[];
@@ -406,7 +410,6 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
   float *stages = wsm;
   float *U = wsm + C::NSTAGE * C::STAGE_FLOATS;
   float *zb = U + C::U_FLOATS;
-  float *dinv = zb + F;
 
   auto fetch = [&]() -> int {
     int v = 0;
@@ -517,10 +520,13 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
       float *xout = X + (row_offset + wi.row) * F;
       if (whole && wi.k0 == wi.k1) {
         // no observations: the reference zeroes the row (_als.pyx:98-100)
-        for (int m = lane; m < F; m += 32) xout[m] = 0.f;
+        for (int m = lane; m < F; m += 32) {
+          xout[m] = 0.f;
+          for (int pi = 0; pi < n_peers; ++pi) peers[pi][(row_offset + wi.row) * F + m] = 0.f;
+        }
       } else if (whole || finish) {
         bool ok = true;
-        if (!(dbg & 8)) factor_solve<NB>(st, U, zb, dinv, xout, lane, ok, dbg);
+        if (!(dbg & 8)) factor_solve<NB>(st, U, zb, xout, lane, ok, dbg, peers, n_peers, (row_offset + wi.row) * F);
         if (!ok && lane == 0) atomicMin(bad_row, (long long)(row_offset + wi.row));
         __syncwarp();
       }
@@ -579,7 +585,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
     ProfScope prof(ctx, kProfCholesky);
     kern<<<grid, 32 * kWarpsPerCta, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
                                                           Cm->work, (int)Cm->n_work, ctx->counters, slots,
-                                                          ctx->bad_row, 0, dbg);
+                                                          ctx->bad_row, 0, dbg, X->peers_dev, X->n_peers);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -589,7 +595,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
     ProfScope prof(ctx, kProfCholFinish);
     kern<<<grid, 32 * kWarpsPerCta, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
                                                           Cm->finish, (int)Cm->n_finish, ctx->counters + 1, slots,
-                                                          ctx->bad_row, 1, dbg);
+                                                          ctx->bad_row, 1, dbg, X->peers_dev, X->n_peers);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }

@@ -27,7 +27,8 @@ template <int T>
 __global__ void __launch_bounds__(kWideThreads)
 cholesky_wide_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
                      float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
-                     const WorkItem *__restrict__ work, int n_work, float *slots, long long *bad_row, int pass) {
+                     const WorkItem *__restrict__ work, int n_work, float *slots, long long *bad_row, int pass,
+                     float *const *peers, int n_peers) {
   using C = WideCfg<T>;
   constexpr int F = C::F, LDA = C::LDA;
   extern __shared__ __align__(16) float smem[];
@@ -45,7 +46,10 @@ cholesky_wide_kernel(const int32_t *__restrict__ indices, const float *__restric
     float *xout = X + (row_offset + wi.row) * F;
     __syncthreads();
     if (whole && wi.k0 == wi.k1) {  // empty row -> zeros (_als.pyx:98-100)
-      for (int m = tid; m < F; m += kWideThreads) xout[m] = 0.f;
+      for (int m = tid; m < F; m += kWideThreads) {
+        xout[m] = 0.f;
+        for (int pi = 0; pi < n_peers; ++pi) peers[pi][(row_offset + wi.row) * F + m] = 0.f;
+      }
       continue;
     }
     float acc[T][T], bacc[T];
@@ -161,7 +165,10 @@ cholesky_wide_kernel(const int32_t *__restrict__ indices, const float *__restric
       for (int i = tid; i < k; i += kWideThreads) bs[i] = fmaf(-As[i * LDA + k], xk, bs[i]);
       __syncthreads();
     }
-    for (int m = tid; m < F; m += kWideThreads) xout[m] = bs[m];
+    for (int m = tid; m < F; m += kWideThreads) {
+      xout[m] = bs[m];
+      for (int pi = 0; pi < n_peers; ++pi) peers[pi][(row_offset + wi.row) * F + m] = bs[m];
+    }
   }
 }
 
@@ -187,7 +194,7 @@ int run_wide(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_factors 
     const int grid = (int)std::min<int64_t>(Cm->n_work, (int64_t)ctx->sm_count * per_sm);
     ProfScope prof(ctx, kProfCholesky);
     kern<<<grid, kWideThreads, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg, Cm->work,
-                                                    (int)Cm->n_work, slots, ctx->bad_row, 0);
+                                                    (int)Cm->n_work, slots, ctx->bad_row, 0, X->peers_dev, X->n_peers);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -195,7 +202,7 @@ int run_wide(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_factors 
     const int grid = (int)std::min<int64_t>(Cm->n_finish, (int64_t)ctx->sm_count * per_sm);
     ProfScope prof(ctx, kProfCholFinish);
     kern<<<grid, kWideThreads, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
-                                                    Cm->finish, (int)Cm->n_finish, slots, ctx->bad_row, 1);
+                                                    Cm->finish, (int)Cm->n_finish, slots, ctx->bad_row, 1, X->peers_dev, X->n_peers);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }

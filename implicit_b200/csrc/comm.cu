@@ -22,6 +22,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -52,6 +53,7 @@ int load_nccl() {
   ALS_SYM(CommDestroy, "ncclCommDestroy")
   ALS_SYM(AllReduce, "ncclAllReduce")
   ALS_SYM(Broadcast, "ncclBroadcast")
+  ALS_SYM(AllGather, "ncclAllGather")
   ALS_SYM(GroupStart, "ncclGroupStart")
   ALS_SYM(GroupEnd, "ncclGroupEnd")
   ALS_SYM(GetErrorString, "ncclGetErrorString")
@@ -143,6 +145,24 @@ ALS_API int als_comm_allreduce_f64(als_ctx *ctx, double *values, int n, int op_m
   ALS_NCCL(g_nccl.AllReduce(ctx->dscalars, ctx->dscalars, n, ncclDouble, op_max ? ncclMax : ncclSum,
                             (ncclComm_t)ctx->comm, ctx->stream));
   ALS_CUDA(cudaMemcpyAsync(values, ctx->dscalars, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ALS_OK;
+}
+
+ALS_API int als_comm_allgather_bytes(als_ctx *ctx, const void *send, void *recv, int nbytes) {
+  ALS_REQUIRE(ctx && send && recv && nbytes > 0 && nbytes <= 256, "als_comm_allgather_bytes: bad argument");
+  if (ctx->world == 1) {
+    memcpy(recv, send, nbytes);
+    return ALS_OK;
+  }
+  ALS_REQUIRE(ctx->comm, "als_comm_allgather_bytes: communicator not initialised");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_scratch(ctx, (int64_t)(ctx->world + 1) * 256);
+  if (rc != ALS_OK) return rc;
+  char *base = (char *)ctx->scratch;
+  ALS_CUDA(cudaMemcpyAsync(base, send, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  ALS_NCCL(g_nccl.AllGather(base, base + 256, nbytes, ncclChar, (ncclComm_t)ctx->comm, ctx->stream));
+  ALS_CUDA(cudaMemcpyAsync(recv, base + 256, (size_t)nbytes * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
   ALS_CUDA(cudaStreamSynchronize(ctx->stream));
   return ALS_OK;
 }

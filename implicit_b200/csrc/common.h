@@ -89,6 +89,11 @@ struct als_factors {
   int f = 0;   // logical factors
   int ld = 0;  // device row stride (multiple of 16, zero padded)
   float *d = nullptr;
+  // peer replicas of the same matrix on the other ranks (CUDA IPC mappings over NVLink): the solve kernels
+  // mirror every row they write into these, which replaces the all-gather after a half-iteration
+  float **peers_dev = nullptr;  // device array of n_peers base pointers (self excluded)
+  int n_peers = 0;
+  std::vector<void *> peer_maps;  // what cudaIpcOpenMemHandle returned, for closing
 };
 
 struct als_csr {

@@ -36,11 +36,14 @@ def check_random_state(random_state):
     return np.random.default_rng(random_state)
 
 
-def nnz_balanced_splits(indptr, parts):
-    """Row boundaries [0 = s_0 <= ... <= s_parts = rows] giving every part ~nnz/parts nonzeros
-    (nnz-balanced, not row-balanced, shards)."""
+def nnz_balanced_splits(indptr, parts, row_cost=0):
+    """Row boundaries [0 = s_0 <= ... <= s_parts = rows] giving every part the same share of
+    nnz + row_cost * rows (nnz-balanced, not row-balanced, shards; row_cost adds the
+    per-row fixed work -- the factorisation -- in units of nonzeros)."""
     indptr = np.asarray(indptr, dtype=np.int64)
     rows = len(indptr) - 1
+    if row_cost:
+        indptr = indptr + row_cost * np.arange(rows + 1, dtype=np.int64)
     nnz = int(indptr[-1] - indptr[0])
     targets = indptr[0] + (nnz * np.arange(1, parts, dtype=np.int64)) // max(parts, 1)
     cuts = np.searchsorted(indptr, targets, side="left")

@@ -162,6 +162,18 @@ int als_comm_destroy(als_ctx *ctx);
 /* All-gather the row shards of a replicated factor matrix: rank r owns rows
  * [row_splits[r], row_splits[r+1]) and every rank ends with all rows. */
 int als_comm_allgather_rows(als_ctx *ctx, als_factors *f, const int64_t *row_splits);
+/* Fused exchange: instead of an all-gather AFTER a half-iteration, the solve kernels store every row they
+ * produce straight into the other ranks' replicas over NVLink (peer memory mapped with CUDA IPC), so the
+ * transfer rides under the compute.  export: this rank's 64-byte handle for f; attach: map the replicas of
+ * all ranks (handles = world * 64 bytes, in rank order); after attach every als_least_squares* call that
+ * writes f mirrors its rows.  The host must still join all ranks (als_sync + als_comm_barrier) before the
+ * next half reads f. */
+#define ALS_IPC_HANDLE_BYTES 64
+int als_factors_ipc_export(als_ctx *ctx, const als_factors *f, void *handle);
+int als_factors_ipc_attach(als_ctx *ctx, als_factors *f, int rank, int world, const void *handles);
+int als_factors_ipc_detach(als_ctx *ctx, als_factors *f);
+/* All-gather nbytes (<= 256) of host data per rank into recv[world * nbytes] (rank order). */
+int als_comm_allgather_bytes(als_ctx *ctx, const void *send, void *recv, int nbytes);
 /* In-place sum / max of n doubles across ranks (host values; used for loss terms and timing). */
 int als_comm_allreduce_f64(als_ctx *ctx, double *values, int n, int op_max);
 int als_comm_barrier(als_ctx *ctx);
