@@ -242,18 +242,21 @@ def run_ours(args):
         if p2p:  # fused exchange: solved rows are stored into the peers' replicas by the solve kernel itself
             ctx.attach_peers(X)
             ctx.attach_peers(Y)
+            _lib.gramian_shard(ctx, Y, isplit[rank], isplit[rank + 1] - isplit[rank])
 
     def half(C, A, B, split):
+        if split is not None and p2p:
+            # device-resident all-reduced Gramian; rows mirrored into the peers by the kernel; the all-reduce
+            # of the next Gramian (over the rows just solved) orders the next half after every peer's stores
+            _lib.half_pregram(ctx, C, A, B, reg, use_cg, 3)
+            _lib.gramian_shard(ctx, A, split[rank], split[rank + 1] - split[rank])
+            return
         if use_cg:
             _lib.least_squares_cg(ctx, C, A, B, reg, 3)
         else:
             _lib.least_squares(ctx, C, A, B, reg)
         if split is not None:
-            if p2p:
-                ctx.sync()
-                ctx.barrier()
-            else:
-                ctx.allgather_rows(A, split)
+            ctx.allgather_rows(A, split)
 
     def iteration():
         half(Cui_s, X, Y, usplit)

@@ -58,6 +58,9 @@ SIGNATURES = {
     "als_gramian": (c_int, [c_void_p, c_void_p, c_void_p]),
     "als_least_squares": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
     "als_least_squares_with_gramian": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
+    "als_gramian_shard": (c_int, [c_void_p, c_void_p, c_i64, c_i64]),
+    "als_least_squares_pregram": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
+    "als_least_squares_cg_pregram": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_int]),
     "als_least_squares_cg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_int]),
     "als_calculate_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, P(c_f64)]),
     "als_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_i64,
@@ -394,6 +397,23 @@ def least_squares(ctx, Cui, X, Y, regularization):
     """_als.least_squares(Cui, X, Y, regularization): raises ValueError like _als.pyx:136-138."""
     bad = c_i64(-1)
     rc = ctx.lib.als_least_squares(ctx.h, Cui.h, X.h, Y.h, float(regularization), ctypes.byref(bad))
+    if rc == ALS_E_NOT_POSDEF:
+        raise ValueError("cholesky failed on row %i. Try increasing the regularization parameter." % bad.value)
+    check(rc)
+
+
+def gramian_shard(ctx, Y, row0, nrows):
+    """Gramian over this rank's rows of Y, summed across ranks, left on the device for the *_pregram solves."""
+    check(ctx.lib.als_gramian_shard(ctx.h, Y.h, int(row0), int(nrows)))
+
+
+def half_pregram(ctx, Cui, X, Y, regularization, use_cg, cg_steps=3):
+    """One half-iteration with the device-resident (already all-reduced) Gramian."""
+    if use_cg:
+        check(ctx.lib.als_least_squares_cg_pregram(ctx.h, Cui.h, X.h, Y.h, float(regularization), int(cg_steps)))
+        return
+    bad = c_i64(-1)
+    rc = ctx.lib.als_least_squares_pregram(ctx.h, Cui.h, X.h, Y.h, float(regularization), ctypes.byref(bad))
     if rc == ALS_E_NOT_POSDEF:
         raise ValueError("cholesky failed on row %i. Try increasing the regularization parameter." % bad.value)
     check(rc)

@@ -177,6 +177,8 @@ class AlternatingLeastSquares:
                 ctx.attach_peers(X)
                 ctx.attach_peers(Y)
                 self._p2p = True
+                # Gramian of the item factors for the first user half (each rank sums its own rows)
+                _lib.gramian_shard(ctx, Y, isplit[pg.rank], isplit[pg.rank + 1] - isplit[pg.rank])
             Cui_s = Cui.slice_rows(usplit[pg.rank], usplit[pg.rank + 1])
             Ciu_s = Ciu.slice_rows(isplit[pg.rank], isplit[pg.rank + 1])
 
@@ -198,6 +200,8 @@ class AlternatingLeastSquares:
                     progress.update(1)
                 if self.calculate_training_loss:
                     loss = self._loss(Cui_s, X, Y, users, items, Cui_host.nnz)
+                    if self._p2p:  # the loss pass reuses the Gramian buffers: restore Y^T Y for the next half
+                        _lib.gramian_shard(ctx, Y, isplit[pg.rank], isplit[pg.rank + 1] - isplit[pg.rank])
                     if progress is not None:
                         progress.set_postfix({"loss": loss})
                     elif not show_progress:
@@ -226,19 +230,25 @@ class AlternatingLeastSquares:
         Cui.close()
         self._check_fit_errors()  # cpu/als.py:202
 
-    def _half(self, C, X, Y, splits):
-        """One half-iteration: solve the rows of (this rank's shard of) C, then exchange them."""
+    def _half(self, C, X, Y, splits, ysplits=None):
+        """One half-iteration: solve the rows of (this rank's shard of) C, then exchange them.
+
+        Multi-GPU (peer replicas attached): the Gramian of Y was accumulated shard-wise and all-reduced by the
+        previous half (`gramian_shard`), the solve kernel stores its rows into every replica, and the
+        all-reduce of the NEXT Gramian -- over the rows this rank just solved -- doubles as the barrier that
+        orders the next half after every peer's stores.  Nothing blocks the host."""
         ctx = self.ctx
+        if splits is not None and self._p2p:
+            rank = self.process_group.rank
+            _lib.half_pregram(ctx, C, X, Y, self.regularization, self.use_cg, self.cg_steps)
+            _lib.gramian_shard(ctx, X, splits[rank], splits[rank + 1] - splits[rank])
+            return
         if self.use_cg:
             _lib.least_squares_cg(ctx, C, X, Y, self.regularization, self.cg_steps)
         else:
             _lib.least_squares(ctx, C, X, Y, self.regularization)
         if splits is not None:
-            if self._p2p:
-                ctx.sync()     # my rows are in every replica ...
-                ctx.barrier()  # ... and so are everybody else's
-            else:
-                ctx.allgather_rows(X, splits)
+            ctx.allgather_rows(X, splits)
 
     def _loss(self, C, X, Y, users, items, nnz):
         ctx = self.ctx

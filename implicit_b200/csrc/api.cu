@@ -637,6 +637,41 @@ ALS_API int als_least_squares(als_ctx *ctx, const als_csr *C, als_factors *X, co
   return finish_cholesky(ctx, C, X, Y, regularization, bad_row);
 }
 
+ALS_API int als_gramian_shard(als_ctx *ctx, const als_factors *Y, int64_t row0, int64_t nrows) {
+  ALS_REQUIRE(ctx && Y, "als_gramian_shard: NULL argument");
+  ALS_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= Y->rows, "als_gramian_shard: rows [%lld, %lld) out of range",
+              (long long)row0, (long long)(row0 + nrows));
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  als_factors view = *Y;  // shallow: a window on Y's rows (no ownership, no peers)
+  view.d = Y->d + row0 * (int64_t)Y->ld;
+  view.rows = nrows;
+  view.peers_dev = nullptr;
+  view.n_peers = 0;
+  view.peer_maps.clear();
+  int rc = launch_gramian(ctx, &view);
+  if (rc != ALS_OK) return rc;
+  return comm_allreduce_gramian(ctx, Y->ld * Y->ld);
+}
+
+ALS_API int als_least_squares_pregram(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
+                                      double regularization, int64_t *bad_row) {
+  int rc = check_half("als_least_squares_pregram", ctx, C, X, Y);
+  if (rc != ALS_OK) return rc;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  return finish_cholesky(ctx, C, X, Y, regularization, bad_row);
+}
+
+ALS_API int als_least_squares_cg_pregram(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
+                                         float regularization, int cg_steps) {
+  int rc = check_half("als_least_squares_cg_pregram", ctx, C, X, Y);
+  if (rc != ALS_OK) return rc;
+  ALS_REQUIRE(cg_steps >= 0, "als_least_squares_cg_pregram: cg_steps < 0");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  rc = launch_regularize(ctx, Y->f, Y->ld, regularization);
+  if (rc != ALS_OK) return rc;
+  return launch_cg(ctx, C, X, Y, cg_steps);
+}
+
 ALS_API int als_least_squares_with_gramian(als_ctx *ctx, const float *YtY_host, const als_csr *C, als_factors *X,
                                            const als_factors *Y, double regularization, int64_t *bad_row) {
   int rc = check_half("als_least_squares_with_gramian", ctx, C, X, Y);

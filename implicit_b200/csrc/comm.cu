@@ -74,6 +74,13 @@ int nccl_fail(ncclResult_t r, const char *what) {
   } while (0)
 
 }  // namespace
+
+int comm_allreduce_gramian(als_ctx *ctx, int n_floats) {
+  if (ctx->world == 1 || !ctx->comm) return ALS_OK;
+  ALS_NCCL(g_nccl.AllReduce(ctx->G, ctx->G, (size_t)n_floats, ncclFloat, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  return ALS_OK;
+}
+
 }  // namespace als
 
 using namespace als;

@@ -131,6 +131,7 @@ int csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out);
 
 // kernels' host launchers (each returns an ALS_* code)
 int launch_gramian(als_ctx *ctx, const als_factors *Y);                  // -> ctx->G
+int comm_allreduce_gramian(als_ctx *ctx, int n_floats);                   // sum ctx->G over ranks (comm.cu)
 int launch_regularize(als_ctx *ctx, int f, int ld, float lambda);         // ctx->G -> ctx->Greg
 int launch_cholesky(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y);
 int launch_cholesky_wide(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y);

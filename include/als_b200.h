@@ -126,6 +126,16 @@ int als_least_squares(als_ctx *ctx, const als_csr *C, als_factors *X, const als_
 int als_least_squares_with_gramian(als_ctx *ctx, const float *YtY_host, const als_csr *C, als_factors *X,
                                    const als_factors *Y, double regularization, int64_t *bad_row);
 
+/* Multi-GPU variants: the Gramian is accumulated over each rank's OWN rows [row0, row0 + nrows) of Y and
+ * summed across ranks (ncclAllReduce of f x f floats on the ctx stream, which also orders this rank after
+ * every peer's preceding solve); als_least_squares*_pregram then solve with that device-resident Gramian
+ * instead of recomputing it from the full replica.  (No reference equivalent.) */
+int als_gramian_shard(als_ctx *ctx, const als_factors *Y, int64_t row0, int64_t nrows);
+int als_least_squares_pregram(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
+                              double regularization, int64_t *bad_row);
+int als_least_squares_cg_pregram(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
+                                 float regularization, int cg_steps);
+
 /* One conjugate-gradient half-iteration, warm-started from X, updated in place.
  * Replaces _als.least_squares_cg(Cui, X, Y, regularization, num_threads, cg_steps),
  * implicit/cpu/_als.pyx:145-248, and LeastSquaresSolver::least_squares (implicit/gpu/als.cu:154-197). */
