@@ -424,10 +424,18 @@ ALS_API int als_csr_download(als_ctx *ctx, const als_csr *csr, int32_t *indptr, 
   ALS_REQUIRE(ctx && csr, "als_csr_download: NULL argument");
   ALS_CUDA(cudaSetDevice(ctx->device));
   ALS_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (indptr) ALS_CUDA(cudaMemcpy(indptr, csr->indptr, sizeof(int32_t) * (csr->rows + 1), cudaMemcpyDeviceToHost));
+  // a row-slice view keeps absolute positions into its parent's arrays: rebase on the way out
+  int32_t base = 0;
+  if (!csr->owns) ALS_CUDA(cudaMemcpy(&base, csr->indptr, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (indptr) {
+    ALS_CUDA(cudaMemcpy(indptr, csr->indptr, sizeof(int32_t) * (csr->rows + 1), cudaMemcpyDeviceToHost));
+    if (base)
+      for (int64_t r = 0; r <= csr->rows; ++r) indptr[r] -= base;
+  }
   if (indices && csr->nnz)
-    ALS_CUDA(cudaMemcpy(indices, csr->indices, sizeof(int32_t) * csr->nnz, cudaMemcpyDeviceToHost));
-  if (data && csr->nnz) ALS_CUDA(cudaMemcpy(data, csr->data, sizeof(float) * csr->nnz, cudaMemcpyDeviceToHost));
+    ALS_CUDA(cudaMemcpy(indices, csr->indices + base, sizeof(int32_t) * csr->nnz, cudaMemcpyDeviceToHost));
+  if (data && csr->nnz)
+    ALS_CUDA(cudaMemcpy(data, csr->data + base, sizeof(float) * csr->nnz, cudaMemcpyDeviceToHost));
   return ALS_OK;
 }
 

@@ -40,7 +40,13 @@ struct TkCfg {
   static constexpr int WX = NW / WY;
   static constexpr int NT = IT / (8 * WX);
   static_assert(WY * WX == NW && NT >= 1 && ROWS_PER_WARP >= 1, "warp tiling");
-  static int smem_floats(int k) { return 2 * QB * LDF + 2 * IT * LDF + QB * SLD + 2 * QB * k + 3 * QB; }
+  // the staged score tile reuses the item buffer the tile's MMAs have just consumed when it fits (F >= 64):
+  // 110 KB instead of 144 KB per CTA, so two CTAs share an SM and one's selection overlaps the other's MMAs
+  static constexpr bool ALIAS_S = (IT * LDF >= QB * SLD);
+  static constexpr int CTAS_PER_SM = (ALIAS_S && F <= 64) ? 2 : 1;
+  static int smem_floats(int k) {
+    return 2 * QB * LDF + 2 * IT * LDF + (ALIAS_S ? 0 : QB * SLD) + 2 * QB * k + 3 * QB;
+  }
 };
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -98,7 +104,7 @@ __device__ __forceinline__ void list_insert(float *ls, int *lc, int &cnt, int k,
 }
 
 template <int F, int TQ>
-__global__ void __launch_bounds__(TkCfg<F, TQ>::THREADS, 1)
+__global__ void __launch_bounds__(TkCfg<F, TQ>::THREADS, TkCfg<F, TQ>::CTAS_PER_SM)
 topk_kernel(const float *__restrict__ items, int n_items, const float *__restrict__ queries,
             const int32_t *__restrict__ query_rows, int n_query, int k, const float *__restrict__ item_norms,
             const uint8_t *__restrict__ item_mask, const int32_t *__restrict__ liked_indptr,
@@ -109,8 +115,8 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
   uint32_t *Qh = reinterpret_cast<uint32_t *>(smem);  // [QB][LDF] query block, TF32 hi part
   uint32_t *Ql = Qh + QB * LDF;                        // [QB][LDF] lo part
   float *Ib = reinterpret_cast<float *>(Ql + QB * LDF);  // [2][IT][LDF] raw item tiles (cp.async double buffer)
-  float *Ss = Ib + 2 * IT * LDF;      // [QB][SLD]
-  float *Ls = Ss + QB * SLD;          // [QB][k]
+  float *Ssep = Ib + 2 * IT * LDF;    // [QB][SLD] separate score tile (only when it cannot alias an item buffer)
+  float *Ls = Ssep + (C::ALIAS_S ? 0 : QB * SLD);  // [QB][k]
   int *Lc = reinterpret_cast<int *>(Ls + QB * k);  // [QB][k]
   int *Cnt = Lc + QB * k;             // [QB]
   int *Cur = Cnt + QB;                // [QB] liked-list cursors
@@ -173,6 +179,7 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
       __syncthreads();
       const float *It = Ib + (tile & 1) * IT * LDF;
+      float *Ss = C::ALIAS_S ? (Ib + (tile & 1) * IT * LDF) : Ssep;
       // ---- scores on the tensor cores: 3xTF32 (lo*hi + hi*lo + hi*hi), fp32 accumulate.
       // Warp (wy, wx) owns queries [16 MT wy, +16 MT) x items [8 NT wx, +8 NT) of the tile.
       float acc[MT][NT][4];
@@ -210,6 +217,7 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
               else mma_tf32(acc[m][n], ah[m][0], ah[m][1], ah[m][2], ah[m][3], bh[n][0], bh[n][1]);
             }
       }
+      if (C::ALIAS_S) __syncthreads();  // every warp is done reading the item tile the scores overwrite
       // ---- norms, global mask, stage the tile (accumulator rows g / g+8, columns 2t, 2t+1)
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
@@ -292,6 +300,7 @@ topk_kernel(const float *__restrict__ items, int n_items, const float *__restric
           __syncwarp();
         }
       }
+      if (C::ALIAS_S) __syncthreads();  // the score tile's buffer is the cp.async target of the tile after next
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     // ---- emit: descending by (score, col) (select.h:33); the tail past cnt stays zero (topk.pyx:20-21)
@@ -343,7 +352,7 @@ int run_topk(als_ctx *ctx, const TopkArgs &a) {
   auto kern = topk_kernel<F, TQ>;
   ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t blocks = ceil_div(a.n_query, C::QB);
-  const int grid = (int)std::min<int64_t>(blocks, (int64_t)ctx->sm_count * 2);
+  const int grid = (int)std::min<int64_t>(blocks, (int64_t)ctx->sm_count * C::CTAS_PER_SM);
   ProfScope prof(ctx, kProfTopk);
   kern<<<grid, C::THREADS, smem, ctx->stream>>>(a.items, a.n_items, a.queries, a.query_rows, a.n_query, a.k, a.norms,
                                                   a.mask, a.liked_indptr, a.liked_indices, a.ids, a.scores);

@@ -405,3 +405,26 @@ def test_c2_full_size_sampled_rows_match_oracle(lib, ctx, orc):
     assert np.median(e_gpu_truth) < max(1e-5, 1.5 * np.median(e_ref_truth))
     assert g_gpu < 1e-6
     assert not np.isnan(got).any()
+
+
+# ---------------------------------------------------------------------------------------- multi-GPU entry points on one GPU
+def test_shard_gramian_pregram_and_slices_match_plain_path(lib, ctx, orc):
+    """als_gramian_shard + als_least_squares*_pregram (the multi-GPU half) on a single rank, over two row
+    slices of the CSR, must reproduce the plain half; a slice view downloads as the rows it covers."""
+    Cui, X, Y = _case(900, 500, 15000, 64, seed=77, orc=orc)
+    for use_cg in (False, True):
+        exp = _gpu_half(lib, ctx, Cui, X, Y, 0.01, use_cg=use_cg)
+        C = lib.DeviceCSR.upload(ctx, Cui)
+        dX, dY = lib.DeviceFactors.from_host(ctx, X), lib.DeviceFactors.from_host(ctx, Y)
+        lib.gramian_shard(ctx, dY, 0, 500)
+        for r0, r1 in ((0, 400), (400, 900)):
+            S = C.slice_rows(r0, r1)
+            lib.half_pregram(ctx, S, dX, dY, 0.01, use_cg, 3)
+            if r0 == 400:
+                got = S.download()
+                ref = Cui[400:900]
+                np.testing.assert_array_equal(got.indptr, ref.indptr)
+                np.testing.assert_array_equal(got.indices, ref.indices)
+                np.testing.assert_array_equal(got.data, ref.data)
+            S.close()
+        np.testing.assert_array_equal(dX.download(), exp)
