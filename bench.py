@@ -57,6 +57,17 @@ def algorithmic_bytes_half(nnz, rows, n_other, f):
     return solve, gram
 
 
+def ncu_traffic(kernel, scale, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the
+    two halves, from the committed ncu capture of this same workload (profiles/ncu_traffic.json, written by
+    tools/ncu_traffic.py).  None when no capture matches the run (other scale / sharded run)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if scale != 1.0 or world != 1 or not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh).get(kernel, {}).get("bytes_per_launch")
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -307,7 +318,7 @@ def run_ours(args):
     achieved = (bytes_per_launch * k_n) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
     roofline = {"bound": "hbm", "kernel": f"{main_kernel}_half_kernel (+ giant-row pass)", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": None, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "traffic": ncu_traffic(main_kernel, args.scale, world), "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": k_ms / k_n if k_n else None,
                 "kernel_share_of_step": k_ms / ms if ms else None,
                 "gramian_ms_per_launch": prof["gramian"][0] / max(prof["gramian"][1], 1)}

@@ -212,6 +212,43 @@ def _ref_ns():
     return _ref
 
 
+def have_ref_evaluation():
+    return bool(glob.glob(os.path.join(_REF_DIR, "evaluation*.so")))
+
+
+_ref_eval = None
+
+
+def ref_evaluation():
+    """The reference's compiled implicit/evaluation.pyx.  It does `from .utils import check_random_state`,
+    so it is loaded as a member of a synthetic package whose `utils` holds that one function."""
+    global _ref_eval
+    if _ref_eval is None:
+        import sys
+
+        if not have_ref_evaluation():
+            raise RuntimeError("oracle/_ref/evaluation*.so is not built (python oracle/build_ref.py --force)")
+        pkg = types.ModuleType("_als_b200_refpkg")
+        pkg.__path__ = [_REF_DIR]
+        utils = types.ModuleType("_als_b200_refpkg.utils")
+
+        def check_random_state(random_state):  # implicit/utils.py:65-83
+            if isinstance(random_state, np.random.RandomState):
+                return np.random.default_rng(random_state.randint(2**31))
+            return np.random.default_rng(random_state)
+
+        utils.check_random_state = check_random_state
+        sys.modules["_als_b200_refpkg"] = pkg
+        sys.modules["_als_b200_refpkg.utils"] = utils
+        path = glob.glob(os.path.join(_REF_DIR, "evaluation*.so"))[0]
+        spec = importlib.util.spec_from_file_location("_als_b200_refpkg.evaluation", path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_als_b200_refpkg.evaluation"] = mod
+        spec.loader.exec_module(mod)
+        _ref_eval = mod
+    return _ref_eval
+
+
 def get(kind="auto"):
     """kind: 'port', 'ref', or 'auto' (ref when built, else port)."""
     if kind == "port":

@@ -1,10 +1,11 @@
 """Build the reference's OWN Cython/OpenMP hot path into oracle/_ref/ (test infrastructure only).
 
 This compiles, unchanged and from where they lie under /root/reference, the two Cython modules that
-ARE the reference hot path:
+ARE the reference hot path, and the evaluation module that drives `recommend` in batches:
 
-  * implicit/cpu/_als.pyx   -> oracle/_ref/_als.*.so   (least_squares, least_squares_cg, calculate_loss)
-  * implicit/cpu/topk.pyx   -> oracle/_ref/topk.*.so   (topk + implicit/cpu/select.h)
+  * implicit/cpu/_als.pyx    -> oracle/_ref/_als.*.so        (least_squares, least_squares_cg, calculate_loss)
+  * implicit/cpu/topk.pyx    -> oracle/_ref/topk.*.so        (topk + implicit/cpu/select.h)
+  * implicit/evaluation.pyx  -> oracle/_ref/evaluation.*.so  (ranking_metrics_at_k, train_test_split)
 
 Nothing from the reference is copied into this repository: the .pyx files are cythonized into a
 scratch directory under /tmp and only the resulting shared objects are written to oracle/_ref/
@@ -30,6 +31,7 @@ REFERENCE = os.environ.get("ALS_B200_REFERENCE", "/root/reference")
 MODULES = {
     "_als": "implicit/cpu/_als.pyx",
     "topk": "implicit/cpu/topk.pyx",
+    "evaluation": "implicit/evaluation.pyx",
 }
 
 

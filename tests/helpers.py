@@ -43,3 +43,30 @@ def load_golden(name):
     Cui = synthetic.power_law_csr(rc["users"], rc["items"], rc["nnz"], rc["seed"], rc["neg"])
     X0, Y0 = synthetic.initial_factors(rc["users"], rc["items"], rc["factors"], seed=42)
     return rc, Cui, X0, Y0, z
+
+
+# ----------------------------------------------------------------------------- evaluation fixtures
+class TableModel:
+    """Stands in for a fitted model: `recommend` returns precomputed ranked ids (no GPU involved)."""
+
+    def __init__(self, table):
+        self.table = table
+
+    def recommend(self, userid, user_items, N=10, **kwargs):
+        ids = self.table[np.asarray(userid)][:, :N]
+        return ids, np.zeros(ids.shape, dtype=np.float32)
+
+
+def eval_case(users, items, K, seed):
+    """Seeded (model, train, test): a random ranking per user, a test CSR with duplicates and empty rows."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(seed)
+    table = np.argsort(rng.random((users, items)), axis=1)[:, :max(K, 1)].astype(np.int32)
+    n = rng.integers(0, min(items, 2 * K) + 1, size=users)
+    n[rng.random(users) < 0.2] = 0  # users without withheld items are skipped (evaluation.pyx:421-422)
+    indptr = np.concatenate([[0], np.cumsum(n)]).astype(np.int32)
+    indices = rng.integers(0, items, size=int(indptr[-1])).astype(np.int32)  # duplicates on purpose
+    test = sp.csr_matrix((np.ones(len(indices), dtype=np.float32), indices, indptr), shape=(users, items))
+    train = sp.random(users, items, density=0.05, format="csr", dtype=np.float32, random_state=seed)
+    return TableModel(table), train, test
