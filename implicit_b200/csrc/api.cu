@@ -38,6 +38,19 @@ int ensure_scratch(als_ctx *ctx, int64_t bytes) {
   return ALS_OK;
 }
 
+int ensure_device_buffer(als_ctx *ctx, void **buf, int64_t *cap, int64_t bytes) {
+  if (bytes <= *cap) return ALS_OK;
+  if (*buf) {
+    ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ALS_CUDA(cudaFree(*buf));
+    *buf = nullptr;
+    *cap = 0;
+  }
+  ALS_CUDA(cudaMalloc(buf, bytes));
+  *cap = bytes;
+  return ALS_OK;
+}
+
 int ensure_pinned(als_ctx *ctx, int64_t bytes) {
   if (bytes <= ctx->pinned_bytes) return ALS_OK;
   if (ctx->pinned) {
@@ -94,6 +107,15 @@ int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr) {
     items.swap(sorted);
   }
   csr->n_work = (int64_t)items.size();
+  for (int c = 0; c < 4; ++c) {
+    int64_t lo = 0, hi = csr->n_work;  // first item of length <= kShortThresholds[c]
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if (items[mid].k1 - items[mid].k0 <= kShortThresholds[c]) hi = mid;
+      else lo = mid + 1;
+    }
+    csr->le_begin[c] = lo;
+  }
   csr->n_finish = (int64_t)fin.size();
   csr->n_slots = slots;
   if (csr->n_work) {
@@ -201,6 +223,7 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   ALS_CUDA(cudaEventCreate(&ctx->ev1));
   ALS_CUDA(cudaMalloc(&ctx->G, sizeof(float) * 256 * 256));
   ALS_CUDA(cudaMalloc(&ctx->Greg, sizeof(float) * 256 * 256));
+  ALS_CUDA(cudaMalloc(&ctx->Pinv, sizeof(float) * 64 * 64));
   ALS_CUDA(cudaMalloc(&ctx->counters, sizeof(int32_t) * 16));
   ALS_CUDA(cudaMalloc(&ctx->bad_row, sizeof(long long) * 2));
   ALS_CUDA(cudaMalloc(&ctx->dscalars, sizeof(double) * 8));
@@ -217,6 +240,9 @@ ALS_API int als_ctx_destroy(als_ctx *ctx) {
   cudaFree(ctx->G);
   cudaFree(ctx->Greg);
   cudaFree(ctx->gram_partials);
+  cudaFree(ctx->Pinv);
+  cudaFree(ctx->whitened);
+  cudaFree(ctx->deferred);
   cudaFree(ctx->counters);
   cudaFree(ctx->bad_row);
   cudaFree(ctx->dscalars);
@@ -513,7 +539,7 @@ ALS_API int als_factors_download(als_ctx *ctx, const als_factors *f, float *host
 ALS_API int als_factors_has_nan(als_ctx *ctx, const als_factors *f, int *has_nan) {
   ALS_REQUIRE(ctx && f && has_nan, "als_factors_has_nan: NULL argument");
   ALS_CUDA(cudaSetDevice(ctx->device));
-  int *flag = reinterpret_cast<int *>(ctx->counters + 8);
+  int *flag = reinterpret_cast<int *>(ctx->counters + kCtrHasNan);
   ALS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
   has_nan_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(f->d, f->rows * (int64_t)f->ld, flag);
   ALS_CUDA(cudaGetLastError());

@@ -65,10 +65,17 @@ struct als_ctx {
   float *Greg = nullptr;
   float *gram_partials = nullptr;
   int64_t gram_partials_cap = 0;
-  // per-launch scalars: [0] work counter, [1] second counter, [2..3] bad row (int64)
+  // per-launch scalars, see the kCtr* slots below (16 ints, zeroed before every half)
   int32_t *counters = nullptr;
   long long *bad_row = nullptr;
   double *dscalars = nullptr;  // loss accumulators (8 doubles)
+  // short-row path of the Cholesky half (cholesky_short.cu): P = R^-1 with G + lambda I = R^T R, the whitened
+  // factors W = Y P, and the list of short items handed back to the full-size kernel
+  float *Pinv = nullptr;
+  float *whitened = nullptr;
+  int64_t whitened_bytes = 0;
+  als::WorkItem *deferred = nullptr;
+  int64_t deferred_cap = 0;
   // generic scratch (giant-row partial slots, L2 flush, top-k staging)
   void *scratch = nullptr;
   int64_t scratch_bytes = 0;
@@ -106,6 +113,8 @@ struct als_csr {
   // schedule
   als::WorkItem *work = nullptr;    // main pass: whole rows + chunks, longest first
   int64_t n_work = 0;
+  // work is sorted by length, so the items of at most 48 / 32 / 16 / 0 nonzeros are suffixes: first index of each
+  int64_t le_begin[4] = {0, 0, 0, 0};
   als::WorkItem *finish = nullptr;  // finish pass: one per giant row (row, first slot, #slots)
   int64_t n_finish = 0;
   int64_t n_slots = 0;
@@ -124,7 +133,15 @@ struct ProfScope {
 };
 enum { kProfGramian = 0, kProfCholesky = 1, kProfCholFinish = 2, kProfCg = 3, kProfCgGiant = 4, kProfTopk = 5, kProfLoss = 6 };
 
+// slots of als_ctx::counters
+enum {
+  kCtrMain = 0, kCtrFinish = 1, kCtrShort = 2 /* +0..2: one per short class */, kCtrDeferredCount = 5,
+  kCtrDeferredWork = 6, kCtrWhitenOk = 7, kCtrHasNan = 8
+};
+constexpr int kShortThresholds[4] = {48, 32, 16, 0};  // als_csr::le_begin[i] <-> length <= kShortThresholds[i]
+
 int ensure_scratch(als_ctx *ctx, int64_t bytes);
+int ensure_device_buffer(als_ctx *ctx, void **buf, int64_t *cap, int64_t bytes);
 int ensure_pinned(als_ctx *ctx, int64_t bytes);
 int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr_host);
 int csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out);
@@ -135,6 +152,10 @@ int comm_allreduce_gramian(als_ctx *ctx, int n_floats);                   // sum
 int launch_regularize(als_ctx *ctx, int f, int ld, float lambda);         // ctx->G -> ctx->Greg
 int launch_cholesky(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y);
 int launch_cholesky_wide(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y);
+// short-row path (cholesky_short.cu).  prepare: P and W from ctx->Greg and Y.  launch: items [begin, n_work) of
+// C->work, all of at most `max_len` nonzeros; whatever it cannot take lands in ctx->deferred / counters[kCtrDeferredCount].
+int short_rows_prepare(als_ctx *ctx, const als_factors *Y);
+int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len);
 int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps);
 int launch_loss(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y, float reg,
                 double *loss);
