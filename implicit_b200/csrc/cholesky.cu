@@ -195,13 +195,9 @@ static int debug_flags() {
 // Longest row (in nonzeros) the short-row path takes: 32 by default; ALS_B200_SHORT_MAX = 0 / 16 / 32 / 48
 // overrides it (0 disables the path; a measurement knob, results agree to fp32 rounding either way).
 static int short_row_limit() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("ALS_B200_SHORT_MAX");
-    const int want = e ? atoi(e) : 32;
-    v = want >= 48 ? 48 : want >= 32 ? 32 : want >= 16 ? 16 : 0;
-  }
-  return v;
+  const char *e = getenv("ALS_B200_SHORT_MAX");  // read per call: tools/short_check.py flips it within a process
+  const int want = e ? atoi(e) : 32;
+  return want >= 48 ? 48 : want >= 32 ? 32 : want >= 16 ? 16 : 0;
 }
 
 template <int NB>

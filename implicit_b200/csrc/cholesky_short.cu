@@ -22,7 +22,7 @@ namespace als {
 
 namespace {
 
-constexpr int kShortWarps = 4;
+constexpr int kShortWarps = 8;
 
 // ---- P = R^-1 in fp64 ---------------------------------------------------------------------------
 // One CTA.  a <- upper Cholesky factor of Greg (right-looking), then column j of P by back substitution.
@@ -148,7 +148,7 @@ __device__ __forceinline__ void short_issue(float *wsm, const float *const (&src
 }
 
 template <int NB, int NBs>
-__global__ void __launch_bounds__(32 * kShortWarps, NBs == 3 ? 1 : 5)
+__global__ void __launch_bounds__(32 * kShortWarps, NBs == 3 ? 2 : NBs == 2 ? 3 : 4)
 short_rows_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ W,
                   const float *__restrict__ P, float *__restrict__ X, int64_t row_offset,
                   const WorkItem *__restrict__ work, int n_work, int32_t *counter, WorkItem *deferred,

@@ -94,4 +94,6 @@ def test_evaluate_fitted_model_against_oracle_ids():
     exp = evaluation_oracle.ranking_metrics_at_k(model, train, test, K=10)
     for k in KEYS:
         assert got[k] == pytest.approx(exp[k], rel=1e-12)
-    assert got["precision"] > 0.5 and got["auc"] > 0.5
+    # likes are random WITHIN a group: of the ~30 unfiltered same-group items ~5 are withheld, so a perfect
+    # group model scores 10 * (5/30) / 5 = 1/3; chance is below 0.02
+    assert got["precision"] > 0.25 and got["auc"] > 0.5
