@@ -219,6 +219,9 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   strncpy(ctx->name, prop.name, sizeof(ctx->name) - 1);
   ALS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ALS_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+  ALS_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+  ALS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  ALS_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   ALS_CUDA(cudaEventCreate(&ctx->ev0));
   ALS_CUDA(cudaEventCreate(&ctx->ev1));
   ALS_CUDA(cudaMalloc(&ctx->G, sizeof(float) * 256 * 256));
@@ -236,6 +239,7 @@ ALS_API int als_ctx_destroy(als_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy);
+  cudaStreamSynchronize(ctx->aux);
   als_comm_destroy(ctx);
   cudaFree(ctx->G);
   cudaFree(ctx->Greg);
@@ -252,6 +256,9 @@ ALS_API int als_ctx_destroy(als_ctx *ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy);
+  cudaStreamDestroy(ctx->aux);
+  cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev_join);
   delete ctx;
   return ALS_OK;
 }

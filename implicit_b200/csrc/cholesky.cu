@@ -192,11 +192,11 @@ static int debug_flags() {
   return v;
 }
 
-// Longest row (in nonzeros) the short-row path takes: 32 by default; ALS_B200_SHORT_MAX = 0 / 16 / 32 / 48
+// Longest row (in nonzeros) the short-row path takes: 48 by default; ALS_B200_SHORT_MAX = 0 / 16 / 32 / 48
 // overrides it (0 disables the path; a measurement knob, results agree to fp32 rounding either way).
 static int short_row_limit() {
   const char *e = getenv("ALS_B200_SHORT_MAX");  // read per call: tools/short_check.py flips it within a process
-  const int want = e ? atoi(e) : 32;
+  const int want = e ? atoi(e) : 48;
   return want >= 48 ? 48 : want >= 32 ? 32 : want >= 16 ? 16 : 0;
 }
 
@@ -234,9 +234,17 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
   if (Cm->n_work) {
     ProfScope prof(ctx, kProfCholesky);
     const int max_grid = ctx->sm_count * ctas_per_sm;
+    // The short-row kernels (and the second pass of the full-size kernel over what they hand back) run on the
+    // aux stream: their CTAs move in as the full-size kernel's persistent CTAs run out of long rows.
+    const bool overlap = short_max > 0 && n_main > 0 && getenv("ALS_B200_SHORT_SERIAL") == nullptr;
+    cudaStream_t side = overlap ? ctx->aux : ctx->stream;
     if (short_max > 0) {
       int rc = short_rows_prepare(ctx, Y);
       if (rc != ALS_OK) return rc;
+      if (overlap) {
+        ALS_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        ALS_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+      }
     }
     if (n_main) {
       const int grid = (int)std::min<int64_t>(ceil_div(n_main, kWarpsPerCta), max_grid);
@@ -247,16 +255,20 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
       ctx->launches++;
     }
     if (short_max > 0) {
-      int rc = short_rows_launch(ctx, Cm, X, Y, n_main, short_max);
+      int rc = short_rows_launch(ctx, Cm, X, Y, n_main, short_max, side);
       if (rc != ALS_OK) return rc;
       // whatever the short-row kernels handed back (negative weights, chunks of giant rows, G not PD)
       const int grid = (int)std::min<int64_t>(ceil_div(Cm->n_work - n_main, kWarpsPerCta), max_grid);
-      kern<<<grid, 32 * kWarpsPerCta, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
-                                                            ctx->deferred, 0, ctx->counters + kCtrDeferredCount,
-                                                            ctx->counters + kCtrDeferredWork, slots, ctx->bad_row, 0,
-                                                            dbg, X->peers_dev, X->n_peers);
+      kern<<<grid, 32 * kWarpsPerCta, smem, side>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
+                                                     ctx->deferred, 0, ctx->counters + kCtrDeferredCount,
+                                                     ctx->counters + kCtrDeferredWork, slots, ctx->bad_row, 0, dbg,
+                                                     X->peers_dev, X->n_peers);
       ALS_CUDA(cudaGetLastError());
       ctx->launches++;
+      if (overlap) {
+        ALS_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
+        ALS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+      }
     }
   }
   if (Cm->n_finish) {

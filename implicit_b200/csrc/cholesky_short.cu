@@ -25,55 +25,61 @@ namespace {
 constexpr int kShortWarps = 8;
 
 // ---- P = R^-1 in fp64 ---------------------------------------------------------------------------
-// One CTA.  a <- upper Cholesky factor of Greg (right-looking), then column j of P by back substitution.
-__global__ void __launch_bounds__(256) whiten_factor_kernel(const float *__restrict__ Greg, int F, float *__restrict__ P,
-                                                            int32_t *ok) {
+// One CTA of 32 x 32 threads on the augmented matrix [G | I] (F x 2F doubles in shared memory).  The row
+// operations of a right-looking Cholesky (scale row k by 1/sqrt(d_k), subtract R[k][i] times row k from every
+// later row i) turn it into [R | L^-1] with G = R^T R, L = R^T; then P = R^-1 = (L^-1)^T.  No dependent chains
+// besides the F pivot steps; every thread owns a fixed 2 x 4 patch of each 32-row / 32-column block.
+__global__ void __launch_bounds__(1024) whiten_factor_kernel(const float *__restrict__ Greg, int F, float *__restrict__ P,
+                                                             int32_t *ok) {
   extern __shared__ __align__(16) unsigned char whiten_smem[];
-  double *a = reinterpret_cast<double *>(whiten_smem);  // [F][F + 1]
-  const int ld = F + 1;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < F * F; e += blockDim.x) a[(e / F) * ld + e % F] = (double)Greg[e];
+  double *a = reinterpret_cast<double *>(whiten_smem);  // [F][2F + 1]
+  const int ld = 2 * F + 1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < F; i += 32)
+    for (int j = tx; j < 2 * F; j += 32) a[i * ld + j] = j < F ? (double)Greg[i * F + j] : (j - F == i ? 1.0 : 0.0);
   __syncthreads();
   for (int k = 0; k < F; ++k) {
     const double d = a[k * ld + k];
-    if (!(d > 0.0) || !(d < 1e300)) {  // same for every thread
-      if (tid == 0) *ok = 0;
+    if (!(d > 0.0) || !(d < 1e300)) {  // same for every thread: G is not positive definite (or not finite)
+      if (threadIdx.x == 0) *ok = 0;
       return;
     }
     const double s = 1.0 / sqrt(d);
     __syncthreads();
-    for (int j = k + tid; j < F; j += blockDim.x) a[k * ld + j] *= s;
+    if (ty == 0)
+      for (int j = tx; j < 2 * F; j += 32)
+        if (j >= k && j <= F + k) a[k * ld + j] *= s;  // R[k][k..F) and L^-1[k][0..k]
     __syncthreads();
-    const int m = F - k - 1;  // trailing block (k, F) x (k, F), upper part
-    for (int e = tid; e < m * m; e += blockDim.x) {
-      const int i = k + 1 + e / m, j = k + 1 + e % m;
-      if (j >= i) a[i * ld + j] -= a[k * ld + i] * a[k * ld + j];
+    for (int i = k + 1 + ty; i < F; i += 32) {
+      const double m = a[k * ld + i];  // R[k][i]
+      for (int j = tx; j < 2 * F; j += 32)
+        if ((j >= i && j < F) || (j >= F && j <= F + k)) a[i * ld + j] -= m * a[k * ld + j];
     }
-    __syncthreads();
+    __syncthreads();  // row k + 1 (the next pivot row) is complete
   }
-  // R P = I, P upper triangular: thread j owns column j
-  for (int j = tid; j < F; j += blockDim.x) {
-    for (int i = F - 1; i > j; --i) P[i * F + j] = 0.f;
-    double col[64];
-#pragma unroll 1
-    for (int i = j; i >= 0; --i) {
-      double acc = (i == j) ? 1.0 : 0.0;
-      for (int k = i + 1; k <= j; ++k) acc -= a[i * ld + k] * col[k];
-      col[i] = acc / a[i * ld + i];
-      P[i * F + j] = (float)col[i];
-    }
-  }
-  if (tid == 0) *ok = 1;
+  for (int i = ty; i < F; i += 32)
+    for (int j = tx; j < F; j += 32) P[i * F + j] = j >= i ? (float)a[j * ld + F + i] : 0.f;  // P[i][j] = L^-1[j][i]
+  if (threadIdx.x == 0) *ok = 1;
 }
 
 // ---- W = Y P ------------------------------------------------------------------------------------
-// 64 rows per CTA pass; thread (ty, tx) owns rows 2 ty, 2 ty + 1 and columns tx CP .. tx CP + CP - 1.
+// 128 rows per CTA pass; thread (ty, tx) owns rows 4 ty .. 4 ty + 3 and, in every 32-column half, columns
+// 4 tx .. 4 tx + 3 (so both the P reads and the W writes of a warp are contiguous and conflict free).
+template <int NB>
+struct WhitenCfg {
+  static constexpr int F = 16 * NB, LDY = F + 1, RT = 128;
+  static constexpr int NH = (F + 31) / 32;  // 32-column halves
+  static constexpr int SMEM_FLOATS = F * F + RT * LDY;
+};
+
 template <int NB>
 __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restrict__ Y, const float *__restrict__ P,
                                                           float *__restrict__ W, int64_t rows) {
-  constexpr int F = 16 * NB, CP = F / 8, LDY = F + 1, RT = 64;
-  __shared__ float Ps[F * F];
-  __shared__ float Ys[RT * LDY];
+  using C = WhitenCfg<NB>;
+  constexpr int F = C::F, LDY = C::LDY, RT = C::RT, NH = C::NH;
+  extern __shared__ __align__(16) unsigned char whiten_rows_smem[];
+  float *Ps = reinterpret_cast<float *>(whiten_rows_smem);
+  float *Ys = Ps + F * F;
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
   for (int e = tid; e < F * F; e += 256) Ps[e] = P[e];
   for (int64_t r0 = (int64_t)blockIdx.x * RT; r0 < rows; r0 += (int64_t)gridDim.x * RT) {
@@ -86,36 +92,58 @@ __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restric
       dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
     }
     __syncthreads();
-    float acc[2][CP];
+    float acc[4][NH][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < CP; ++j) acc[i][j] = 0.f;
-#pragma unroll 8
+      for (int h = 0; h < NH; ++h) acc[i][h][0] = acc[i][h][1] = acc[i][h][2] = acc[i][h][3] = 0.f;
+#pragma unroll 4
     for (int k = 0; k < F; ++k) {
-      float y[2], p[CP];
+      float y[4];
+      float4 p[NH];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) y[i] = Ys[(2 * ty + i) * LDY + k];
+      for (int i = 0; i < 4; ++i) y[i] = Ys[(4 * ty + i) * LDY + k];
 #pragma unroll
-      for (int j = 0; j < CP; j += 2) {
-        const float2 v = *reinterpret_cast<const float2 *>(Ps + k * F + tx * CP + j);
-        p[j] = v.x; p[j + 1] = v.y;
+      for (int h = 0; h < NH; ++h) {
+        const int c = 32 * h + 4 * tx;
+        p[h] = c < F ? *reinterpret_cast<const float4 *>(Ps + k * F + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < CP; ++j) acc[i][j] = fmaf(y[i], p[j], acc[i][j]);
+        for (int h = 0; h < NH; ++h) {
+          acc[i][h][0] = fmaf(y[i], p[h].x, acc[i][h][0]);
+          acc[i][h][1] = fmaf(y[i], p[h].y, acc[i][h][1]);
+          acc[i][h][2] = fmaf(y[i], p[h].z, acc[i][h][2]);
+          acc[i][h][3] = fmaf(y[i], p[h].w, acc[i][h][3]);
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int64_t r = r0 + 2 * ty + i;
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + 4 * ty + i;
       if (r < rows) {
 #pragma unroll
-        for (int j = 0; j < CP; j += 2)
-          *reinterpret_cast<float2 *>(W + r * F + tx * CP + j) = make_float2(acc[i][j], acc[i][j + 1]);
+        for (int h = 0; h < NH; ++h) {
+          const int c = 32 * h + 4 * tx;
+          if (c < F)
+            *reinterpret_cast<float4 *>(W + r * F + c) = make_float4(acc[i][h][0], acc[i][h][1], acc[i][h][2], acc[i][h][3]);
+        }
       }
     }
   }
+}
+
+template <int NB>
+int run_whiten_rows(als_ctx *ctx, const als_factors *Y) {
+  using C = WhitenCfg<NB>;
+  const int smem = C::SMEM_FLOATS * (int)sizeof(float);
+  auto kern = whiten_rows_kernel<NB>;
+  ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), C::RT), (int64_t)ctx->sm_count * 4);
+  kern<<<grid, 256, smem, ctx->stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
+  ALS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return ALS_OK;
 }
 
 // ---- the short-row solver -----------------------------------------------------------------------
@@ -344,7 +372,7 @@ short_rows_kernel(const int32_t *__restrict__ indices, const float *__restrict__
 }
 
 template <int NB, int NBs>
-int run_short(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, int64_t count, int slot) {
+int run_short(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, int64_t count, int slot, cudaStream_t stream) {
   using C = ShortCfg<NB, NBs>;
   if (count <= 0) return ALS_OK;
   const int smem = C::SMEM_FLOATS * (int)sizeof(float);
@@ -357,7 +385,7 @@ int run_short(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, in
     return ALS_E_CUDA;
   }
   const int grid = (int)std::min<int64_t>(ceil_div(count, kShortWarps), (int64_t)ctx->sm_count * ctas_per_sm);
-  kern<<<grid, 32 * kShortWarps, smem, ctx->stream>>>(Cm->indices, Cm->data, ctx->whitened, ctx->Pinv, X->d, Cm->row_offset,
+  kern<<<grid, 32 * kShortWarps, smem, stream>>>(Cm->indices, Cm->data, ctx->whitened, ctx->Pinv, X->d, Cm->row_offset,
                                                        Cm->work + begin, (int)count, ctx->counters + kCtrShort + slot,
                                                        ctx->deferred, ctx->counters + kCtrDeferredCount,
                                                        ctx->counters + kCtrWhitenOk, X->peers_dev, X->n_peers);
@@ -368,7 +396,7 @@ int run_short(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, in
 
 // items [begin, n_work) split into the classes (32, 48], (16, 32], [0, 16] by the schedule's suffix offsets
 template <int NB>
-int run_short_classes(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, int max_len) {
+int run_short_classes(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, int max_len, cudaStream_t stream) {
   const int64_t b48 = std::max(begin, Cm->le_begin[0]), b32 = std::max(begin, Cm->le_begin[1]),
                 b16 = std::max(begin, Cm->le_begin[2]);
   int rc = ALS_OK;
@@ -377,14 +405,14 @@ int run_short_classes(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t b
     return ALS_E_INVALID;
   }
   if constexpr (NB >= 4) {
-    if (max_len > 32) rc = run_short<NB, 3>(ctx, Cm, X, b48, b32 - b48, 0);
+    if (max_len > 32) rc = run_short<NB, 3>(ctx, Cm, X, b48, b32 - b48, 0, stream);
     if (rc != ALS_OK) return rc;
   }
   if constexpr (NB >= 3) {
-    if (max_len > 16) rc = run_short<NB, 2>(ctx, Cm, X, b32, b16 - b32, 1);
+    if (max_len > 16) rc = run_short<NB, 2>(ctx, Cm, X, b32, b16 - b32, 1, stream);
     if (rc != ALS_OK) return rc;
   }
-  return run_short<NB, 1>(ctx, Cm, X, b16, Cm->n_work - b16, 2);
+  return run_short<NB, 1>(ctx, Cm, X, b16, Cm->n_work - b16, 2, stream);
 }
 
 }  // namespace
@@ -398,33 +426,31 @@ int short_rows_prepare(als_ctx *ctx, const als_factors *Y) {
   int rc = ensure_device_buffer(ctx, (void **)&ctx->whitened, &ctx->whitened_bytes,
                                 std::max<int64_t>(Y->rows, 1) * F * (int64_t)sizeof(float));
   if (rc != ALS_OK) return rc;
-  const int smem = F * (F + 1) * (int)sizeof(double);
-  whiten_factor_kernel<<<1, 256, smem, ctx->stream>>>(ctx->Greg, F, ctx->Pinv, ctx->counters + kCtrWhitenOk);
+  const int smem = F * (2 * F + 1) * (int)sizeof(double);
+  ALS_CUDA(cudaFuncSetAttribute(whiten_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  whiten_factor_kernel<<<1, 1024, smem, ctx->stream>>>(ctx->Greg, F, ctx->Pinv, ctx->counters + kCtrWhitenOk);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
-  const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), 64), (int64_t)ctx->sm_count * 4);
   switch (F / 16) {
-    case 2: whiten_rows_kernel<2><<<grid, 256, 0, ctx->stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows); break;
-    case 3: whiten_rows_kernel<3><<<grid, 256, 0, ctx->stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows); break;
-    case 4: whiten_rows_kernel<4><<<grid, 256, 0, ctx->stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows); break;
+    case 2: return run_whiten_rows<2>(ctx, Y);
+    case 3: return run_whiten_rows<3>(ctx, Y);
+    case 4: return run_whiten_rows<4>(ctx, Y);
     default:
       set_error("short rows: padded factors %d not supported", F);
       return ALS_E_UNSUPPORTED;
   }
-  ALS_CUDA(cudaGetLastError());
-  ctx->launches++;
-  return ALS_OK;
 }
 
-int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len) {
+int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len,
+                      cudaStream_t stream) {
   const int64_t count = C->n_work - begin;
   if (count <= 0) return ALS_OK;
   int rc = ensure_device_buffer(ctx, (void **)&ctx->deferred, &ctx->deferred_cap, count * (int64_t)sizeof(WorkItem));
   if (rc != ALS_OK) return rc;
   switch (Y->ld / 16) {
-    case 2: return run_short_classes<2>(ctx, C, X, begin, max_len);
-    case 3: return run_short_classes<3>(ctx, C, X, begin, max_len);
-    case 4: return run_short_classes<4>(ctx, C, X, begin, max_len);
+    case 2: return run_short_classes<2>(ctx, C, X, begin, max_len, stream);
+    case 3: return run_short_classes<3>(ctx, C, X, begin, max_len, stream);
+    case 4: return run_short_classes<4>(ctx, C, X, begin, max_len, stream);
     default:
       set_error("short rows: padded factors %d not supported", Y->ld);
       return ALS_E_UNSUPPORTED;

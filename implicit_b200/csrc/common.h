@@ -58,6 +58,8 @@ struct als_ctx {
   char name[256] = {0};
   cudaStream_t stream = nullptr;   // compute
   cudaStream_t copy = nullptr;     // H2D / D2H staging
+  cudaStream_t aux = nullptr;      // short-row kernels of a Cholesky half, concurrent with the full-size kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   // Gramian state: G (f_pad x f_pad, without lambda) and Greg (G + lambda I, identity on padded dims)
@@ -155,7 +157,8 @@ int launch_cholesky_wide(als_ctx *ctx, const als_csr *C, als_factors *X, const a
 // short-row path (cholesky_short.cu).  prepare: P and W from ctx->Greg and Y.  launch: items [begin, n_work) of
 // C->work, all of at most `max_len` nonzeros; whatever it cannot take lands in ctx->deferred / counters[kCtrDeferredCount].
 int short_rows_prepare(als_ctx *ctx, const als_factors *Y);
-int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len);
+int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len,
+                      cudaStream_t stream);
 int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps);
 int launch_loss(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y, float reg,
                 double *loss);

@@ -18,8 +18,11 @@ print(f"C2 x{scale}: user rows <=16: {(deg<=16).sum()}, <=32: {(deg<=32).sum()},
 sample = np.arange(0, cfg["users"], 197)
 truth = None
 base = None
-for lim in (sys.argv[1:] or ["0", "16", "32", "48"]):
-    os.environ["ALS_B200_SHORT_MAX"] = lim
+for lim in (sys.argv[1:] or ["0", "32", "48s", "48"]):
+    os.environ["ALS_B200_SHORT_MAX"] = lim.rstrip("s")
+    os.environ.pop("ALS_B200_SHORT_SERIAL", None)
+    if lim.endswith("s"):  # "48s": short-row kernels serialised behind the full-size kernel (no aux stream)
+        os.environ["ALS_B200_SHORT_SERIAL"] = "1"
     ctx.profile(True)
     for it in range(4):  # 3 timed cold-start iterations (same state every time, like bench.py's device arm)
         X.upload(X0); Y.upload(Y0)
