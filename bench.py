@@ -316,7 +316,8 @@ def run_ours(args):
     bytes_per_launch = (su + si + extra) / 2.0
     peak, peak_src = measured_peak_gbs()
     achieved = (bytes_per_launch * k_n) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": f"{main_kernel}_half_kernel (+ giant-row pass)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": ("cholesky half: cholesky_half_kernel (rows > 48 nnz) + short_rows_kernel<4,{3,2,1}> + whitening + giant-row pass"
+                           if not use_cg else "cg_rows_kernel (+ giant-row passes)"), "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "traffic": ncu_traffic(main_kernel, args.scale, world), "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": k_ms / k_n if k_n else None,

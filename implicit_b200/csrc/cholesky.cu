@@ -234,17 +234,18 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
   if (Cm->n_work) {
     ProfScope prof(ctx, kProfCholesky);
     const int max_grid = ctx->sm_count * ctas_per_sm;
-    // The short-row kernels (and the second pass of the full-size kernel over what they hand back) run on the
-    // aux stream: their CTAs move in as the full-size kernel's persistent CTAs run out of long rows.
+    // The short-row side (whitening, the short-row kernels, the second pass of the full-size kernel over what they
+    // hand back) runs on the aux stream.  The single-CTA factorisation of G is launched first and hides behind the
+    // full-size kernel; the rest moves in as that kernel's persistent CTAs run out of long rows.
     const bool overlap = short_max > 0 && n_main > 0 && getenv("ALS_B200_SHORT_SERIAL") == nullptr;
     cudaStream_t side = overlap ? ctx->aux : ctx->stream;
     if (short_max > 0) {
-      int rc = short_rows_prepare(ctx, Y);
-      if (rc != ALS_OK) return rc;
       if (overlap) {
         ALS_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
         ALS_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
       }
+      int rc = short_rows_prepare(ctx, Y, side);
+      if (rc != ALS_OK) return rc;
     }
     if (n_main) {
       const int grid = (int)std::min<int64_t>(ceil_div(n_main, kWarpsPerCta), max_grid);

@@ -25,10 +25,9 @@ namespace {
 constexpr int kShortWarps = 8;
 
 // ---- P = R^-1 in fp64 ---------------------------------------------------------------------------
-// One CTA of 32 x 32 threads on the augmented matrix [G | I] (F x 2F doubles in shared memory).  The row
-// operations of a right-looking Cholesky (scale row k by 1/sqrt(d_k), subtract R[k][i] times row k from every
-// later row i) turn it into [R | L^-1] with G = R^T R, L = R^T; then P = R^-1 = (L^-1)^T.  No dependent chains
-// besides the F pivot steps; every thread owns a fixed 2 x 4 patch of each 32-row / 32-column block.
+// One CTA of 32 x 32 threads on the augmented matrix [G | I] (F x 2F doubles in shared memory).  Gaussian
+// elimination without pivoting (G is SPD) turns it into [D U | L1^-1] with G = U^T D U, U unit upper triangular,
+// L1 = U^T; then R = D^1/2 U and P = R^-1 = (D^-1/2 L1^-1)^T.  One barrier per pivot: step k only reads row k.
 __global__ void __launch_bounds__(1024) whiten_factor_kernel(const float *__restrict__ Greg, int F, float *__restrict__ P,
                                                              int32_t *ok) {
   extern __shared__ __align__(16) unsigned char whiten_smem[];
@@ -40,25 +39,28 @@ __global__ void __launch_bounds__(1024) whiten_factor_kernel(const float *__rest
   __syncthreads();
   for (int k = 0; k < F; ++k) {
     const double d = a[k * ld + k];
-    if (!(d > 0.0) || !(d < 1e300)) {  // same for every thread: G is not positive definite (or not finite)
+    // same for every thread: G is not positive definite, not finite, or out of the range the fp32 seed covers
+    if (!(d > 1e-30) || !(d < 1e30)) {
       if (threadIdx.x == 0) *ok = 0;
       return;
     }
-    const double s = 1.0 / sqrt(d);
-    __syncthreads();
-    if (ty == 0)
-      for (int j = tx; j < 2 * F; j += 32)
-        if (j >= k && j <= F + k) a[k * ld + j] *= s;  // R[k][k..F) and L^-1[k][0..k]
-    __syncthreads();
+    double rinv = (double)(1.f / (float)d);  // seed + two Newton steps: full double precision
+    rinv = rinv * (2.0 - d * rinv);
+    rinv = rinv * (2.0 - d * rinv);
     for (int i = k + 1 + ty; i < F; i += 32) {
-      const double m = a[k * ld + i];  // R[k][i]
+      const double m = a[k * ld + i] * rinv;  // G is symmetric: the multiplier of row i is (D U)[k][i] / d_k
       for (int j = tx; j < 2 * F; j += 32)
         if ((j >= i && j < F) || (j >= F && j <= F + k)) a[i * ld + j] -= m * a[k * ld + j];
     }
     __syncthreads();  // row k + 1 (the next pivot row) is complete
   }
-  for (int i = ty; i < F; i += 32)
-    for (int j = tx; j < F; j += 32) P[i * F + j] = j >= i ? (float)a[j * ld + F + i] : 0.f;  // P[i][j] = L^-1[j][i]
+  for (int j = ty; j < F; j += 32) {  // row j of L1^-1 scaled by d_j^-1/2 is column j of P
+    const double d = a[j * ld + j];
+    double s = (double)rsqrtf((float)d);
+    s = s * (1.5 - 0.5 * d * s * s);
+    s = s * (1.5 - 0.5 * d * s * s);
+    for (int i = tx; i < F; i += 32) P[i * F + j] = i <= j ? (float)(a[j * ld + F + i] * s) : 0.f;
+  }
   if (threadIdx.x == 0) *ok = 1;
 }
 
@@ -97,26 +99,30 @@ __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restric
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int h = 0; h < NH; ++h) acc[i][h][0] = acc[i][h][1] = acc[i][h][2] = acc[i][h][3] = 0.f;
+    // P is upper triangular: row k only reaches the 32-column halves h >= k / 32
+#pragma unroll
+    for (int kb = 0; kb < NH; ++kb) {
 #pragma unroll 4
-    for (int k = 0; k < F; ++k) {
-      float y[4];
-      float4 p[NH];
+      for (int k = 32 * kb; k < (32 * kb + 32 < F ? 32 * kb + 32 : F); ++k) {
+        float y[4];
+        float4 p[NH];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = Ys[(4 * ty + i) * LDY + k];
+        for (int i = 0; i < 4; ++i) y[i] = Ys[(4 * ty + i) * LDY + k];
 #pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        const int c = 32 * h + 4 * tx;
-        p[h] = c < F ? *reinterpret_cast<const float4 *>(Ps + k * F + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          acc[i][h][0] = fmaf(y[i], p[h].x, acc[i][h][0]);
-          acc[i][h][1] = fmaf(y[i], p[h].y, acc[i][h][1]);
-          acc[i][h][2] = fmaf(y[i], p[h].z, acc[i][h][2]);
-          acc[i][h][3] = fmaf(y[i], p[h].w, acc[i][h][3]);
+        for (int h = kb; h < NH; ++h) {
+          const int c = 32 * h + 4 * tx;
+          p[h] = c < F ? *reinterpret_cast<const float4 *>(Ps + k * F + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int h = kb; h < NH; ++h) {
+            acc[i][h][0] = fmaf(y[i], p[h].x, acc[i][h][0]);
+            acc[i][h][1] = fmaf(y[i], p[h].y, acc[i][h][1]);
+            acc[i][h][2] = fmaf(y[i], p[h].z, acc[i][h][2]);
+            acc[i][h][3] = fmaf(y[i], p[h].w, acc[i][h][3]);
+          }
+      }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -134,13 +140,13 @@ __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restric
 }
 
 template <int NB>
-int run_whiten_rows(als_ctx *ctx, const als_factors *Y) {
+int run_whiten_rows(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) {
   using C = WhitenCfg<NB>;
   const int smem = C::SMEM_FLOATS * (int)sizeof(float);
   auto kern = whiten_rows_kernel<NB>;
   ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), C::RT), (int64_t)ctx->sm_count * 4);
-  kern<<<grid, 256, smem, ctx->stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
+  kern<<<grid, 256, smem, stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
   return ALS_OK;
@@ -333,7 +339,7 @@ short_rows_kernel(const int32_t *__restrict__ indices, const float *__restrict__
     for (int sl = 0; sl < NL; ++sl) {
       const float tc = ew[sl] * s[sl];
       const int cnt = min(32, n - 32 * sl);
-#pragma unroll 4
+#pragma unroll 8
       for (int i = 0; i < cnt; ++i) {
         const float ti = __shfl_sync(0xffffffffu, tc, i);
         const int ri = __shfl_sync(0xffffffffu, idx[sl], i);
@@ -417,7 +423,7 @@ int run_short_classes(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t b
 
 }  // namespace
 
-int short_rows_prepare(als_ctx *ctx, const als_factors *Y) {
+int short_rows_prepare(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) {
   const int F = Y->ld;
   if (F > 64) {
     set_error("short rows: factors beyond 64 are not supported");
@@ -428,13 +434,13 @@ int short_rows_prepare(als_ctx *ctx, const als_factors *Y) {
   if (rc != ALS_OK) return rc;
   const int smem = F * (2 * F + 1) * (int)sizeof(double);
   ALS_CUDA(cudaFuncSetAttribute(whiten_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  whiten_factor_kernel<<<1, 1024, smem, ctx->stream>>>(ctx->Greg, F, ctx->Pinv, ctx->counters + kCtrWhitenOk);
+  whiten_factor_kernel<<<1, 1024, smem, stream>>>(ctx->Greg, F, ctx->Pinv, ctx->counters + kCtrWhitenOk);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
   switch (F / 16) {
-    case 2: return run_whiten_rows<2>(ctx, Y);
-    case 3: return run_whiten_rows<3>(ctx, Y);
-    case 4: return run_whiten_rows<4>(ctx, Y);
+    case 2: return run_whiten_rows<2>(ctx, Y, stream);
+    case 3: return run_whiten_rows<3>(ctx, Y, stream);
+    case 4: return run_whiten_rows<4>(ctx, Y, stream);
     default:
       set_error("short rows: padded factors %d not supported", F);
       return ALS_E_UNSUPPORTED;

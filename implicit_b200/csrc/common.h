@@ -156,7 +156,7 @@ int launch_cholesky(als_ctx *ctx, const als_csr *C, als_factors *X, const als_fa
 int launch_cholesky_wide(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y);
 // short-row path (cholesky_short.cu).  prepare: P and W from ctx->Greg and Y.  launch: items [begin, n_work) of
 // C->work, all of at most `max_len` nonzeros; whatever it cannot take lands in ctx->deferred / counters[kCtrDeferredCount].
-int short_rows_prepare(als_ctx *ctx, const als_factors *Y);
+int short_rows_prepare(als_ctx *ctx, const als_factors *Y, cudaStream_t stream);
 int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len,
                       cudaStream_t stream);
 int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps);
