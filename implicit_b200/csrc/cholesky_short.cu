@@ -139,14 +139,115 @@ __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restric
   }
 }
 
+// ---- W = Y P on the tensor cores ------------------------------------------------------------------
+// Warp per 16-row tile: A = the tile of Y (cp.async, double buffered), B = P pre-split into TF32 hi / lo parts in
+// shared memory, 3xTF32 mma.sync, triangular P: k-step s only reaches the 8-column tiles j >= s.  Memory-bound.
+constexpr int kWhitenWarps = 8;
+
+template <int NB>
+struct WhitenMmaCfg {
+  static constexpr int F = 16 * NB, NT8 = 2 * NB;
+  static constexpr int LDY = F + 4;   // A-fragment reads conflict free
+  static constexpr int LDP = F + 8;   // B-fragment reads conflict free
+  static constexpr int TILE = 16 * LDY;
+  static constexpr int SMEM_FLOATS = 2 * F * LDP + kWhitenWarps * 2 * TILE;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(32 * kWhitenWarps, 2)
+whiten_rows_mma_kernel(const float *__restrict__ Y, const float *__restrict__ P, float *__restrict__ W, int64_t rows) {
+  using C = WhitenMmaCfg<NB>;
+  constexpr int F = C::F, NT8 = C::NT8, LDY = C::LDY, LDP = C::LDP;
+  extern __shared__ __align__(16) unsigned char whiten_mma_smem[];
+  uint32_t *Ph = reinterpret_cast<uint32_t *>(whiten_mma_smem);
+  uint32_t *Pl = Ph + F * LDP;
+  float *tiles = reinterpret_cast<float *>(Pl + F * LDP);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int e = threadIdx.x; e < F * F; e += blockDim.x) {
+    uint32_t hi, lo;
+    split_tf32(__ldg(P + e), hi, lo);
+    Ph[(e / F) * LDP + e % F] = hi;
+    Pl[(e / F) * LDP + e % F] = lo;
+  }
+  __syncthreads();
+  float *mine = tiles + warp * 2 * C::TILE;
+  const int64_t ntiles = (rows + 15) >> 4;
+  const int64_t stride = (int64_t)gridDim.x * kWhitenWarps;
+  auto issue = [&](int64_t tile, int buf) {
+    if (tile < ntiles) {
+      float *st = mine + buf * C::TILE;
+      constexpr int CH = F / 4;
+#pragma unroll
+      for (int q = 0; q < 2 * NB; ++q) {  // 16 rows x F/4 chunks = 64 NB chunks
+        const int id = q * 32 + lane, row = id / CH, ch = id % CH;
+        int64_t r = tile * 16 + row;
+        if (r >= rows) r = rows - 1;  // clamp: the duplicate rows are never stored
+        cp_async16(st + row * LDY + ch * 4, Y + r * F + ch * 4);
+      }
+    }
+    cp_async_commit();
+  };
+  int64_t tile = (int64_t)blockIdx.x * kWhitenWarps + warp;
+  issue(tile, 0);
+  int buf = 0;
+  for (; tile < ntiles; tile += stride) {
+    issue(tile + stride, buf ^ 1);
+    cp_async_wait<1>();
+    __syncwarp();
+    const float *st = mine + buf * C::TILE;
+    float acc[NT8][4];
+#pragma unroll
+    for (int j = 0; j < NT8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int s = 0; s < NT8; ++s) {  // k-step: factor dimensions 8s .. 8s+7
+      uint32_t ah[4], al[4];
+      split_tf32(st[g * LDY + 8 * s + t], ah[0], al[0]);
+      split_tf32(st[(g + 8) * LDY + 8 * s + t], ah[1], al[1]);
+      split_tf32(st[g * LDY + 8 * s + t + 4], ah[2], al[2]);
+      split_tf32(st[(g + 8) * LDY + 8 * s + t + 4], ah[3], al[3]);
+#pragma unroll
+      for (int j = s; j < NT8; ++j) {
+        const uint32_t bh0 = Ph[(8 * s + t) * LDP + 8 * j + g], bh1 = Ph[(8 * s + t + 4) * LDP + 8 * j + g];
+        const uint32_t bl0 = Pl[(8 * s + t) * LDP + 8 * j + g], bl1 = Pl[(8 * s + t + 4) * LDP + 8 * j + g];
+        mma_tf32(acc[j], al[0], al[1], al[2], al[3], bh0, bh1);
+        mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+        mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+      }
+    }
+    const int64_t r0 = tile * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < NT8; ++j) {
+      if (r0 < rows) *reinterpret_cast<float2 *>(W + r0 * F + 8 * j + 2 * t) = make_float2(acc[j][0], acc[j][1]);
+      if (r1 < rows) *reinterpret_cast<float2 *>(W + r1 * F + 8 * j + 2 * t) = make_float2(acc[j][2], acc[j][3]);
+    }
+    __syncwarp();  // everyone is done with this buffer before the next iteration refills it
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
 template <int NB>
 int run_whiten_rows(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) {
-  using C = WhitenCfg<NB>;
-  const int smem = C::SMEM_FLOATS * (int)sizeof(float);
-  auto kern = whiten_rows_kernel<NB>;
-  ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), C::RT), (int64_t)ctx->sm_count * 4);
-  kern<<<grid, 256, smem, stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
+  // Default: fp32 FMA (round-to-nearest accumulation).  The mma.sync version below is ~40 us faster per half on C2
+  // but the tensor core truncates its accumulator on every add: measured 3x the error on short rows (7e-6 vs 2e-6
+  // against an fp64 solve), so it stays behind ALS_B200_WHITEN_MMA.
+  if (!getenv("ALS_B200_WHITEN_MMA")) {
+    using C = WhitenCfg<NB>;
+    const int smem = C::SMEM_FLOATS * (int)sizeof(float);
+    auto kern = whiten_rows_kernel<NB>;
+    ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), C::RT), (int64_t)ctx->sm_count * 4);
+    kern<<<grid, 256, smem, stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
+  } else {
+    using C = WhitenMmaCfg<NB>;
+    const int smem = C::SMEM_FLOATS * (int)sizeof(float);
+    auto kern = whiten_rows_mma_kernel<NB>;
+    ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), 16 * kWhitenWarps),
+                                            (int64_t)ctx->sm_count * 2);
+    kern<<<grid, 32 * kWhitenWarps, smem, stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
+  }
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
   return ALS_OK;
