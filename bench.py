@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--trace-e2e", action="store_true", help="cProfile of the last end-to-end fit, to stderr")
     return ap.parse_args()
 
 
@@ -342,10 +343,22 @@ def run_ours(args):
             m.user_factors, m.item_factors = X0p, Y0p
             if world > 1:
                 pg.barrier()
+            prof_e2e = None
+            if args.trace_e2e and rep == reps:
+                import cProfile
+
+                prof_e2e = cProfile.Profile()
+                prof_e2e.enable()
             t = time.perf_counter()
             m.fit(Cpin, show_progress=False)
             _ = m.user_factors, m.item_factors  # D2H
             dt = time.perf_counter() - t
+            if prof_e2e is not None:
+                import pstats
+
+                prof_e2e.disable()
+                print(f"e2e fit: {dt * 1e3:.2f} ms; all reps so far {[round(x * 1e3, 2) for x in times]}", file=sys.stderr)
+                pstats.Stats(prof_e2e, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
             if rep > 0:  # first repetition is warm-up
                 times.append(pg.allreduce_max(dt) if world > 1 else dt)
         e2e = {"value": (users + items) * E2E_ITERS / float(np.mean(times)), "unit": UNIT,

@@ -24,6 +24,24 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   return ALS_E_CUDA;
 }
 
+int dev_alloc(als_ctx *ctx, void **ptr, int64_t bytes, cudaStream_t stream) {
+  ALS_CUDA(cudaMallocAsync(ptr, (size_t)std::max<int64_t>(bytes, 16), stream ? stream : ctx->stream));
+  return ALS_OK;
+}
+
+void dev_free(als_ctx *ctx, void *ptr) {
+  if (ptr) cudaFreeAsync(ptr, ctx->stream);
+}
+
+// Builds the schedule of a device-transposed CSR from the indptr copy that csr_transpose left in flight.
+int ensure_schedule(als_ctx *ctx, als_csr *csr) {
+  if (!csr->sched_pending) return ALS_OK;
+  ALS_CUDA(cudaEventSynchronize(ctx->sched_ev));
+  csr->sched_pending = false;
+  ctx->sched_owner = nullptr;
+  return build_schedule(ctx, csr, ctx->sched_pinned);
+}
+
 int ensure_scratch(als_ctx *ctx, int64_t bytes) {
   if (bytes <= ctx->scratch_bytes) return ALS_OK;
   if (ctx->scratch) {
@@ -118,25 +136,27 @@ int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr) {
   }
   csr->n_finish = (int64_t)fin.size();
   csr->n_slots = slots;
+  // The lists are allocated and uploaded on the copy stream: when the schedule of a transposed matrix is built
+  // lazily, a half-iteration is already running on the compute stream and must not delay them (nor they it).
+  cudaStream_t up = ctx->copy;
+  int rc;
   if (csr->n_work) {
-    ALS_CUDA(cudaMalloc(&csr->work, sizeof(WorkItem) * items.size()));
-    ALS_CUDA(cudaMemcpyAsync(csr->work, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice,
-                             ctx->stream));
+    if ((rc = dev_alloc(ctx, (void **)&csr->work, sizeof(WorkItem) * items.size(), up)) != ALS_OK) return rc;
+    ALS_CUDA(cudaMemcpyAsync(csr->work, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, up));
   }
   if (csr->n_finish) {
-    ALS_CUDA(cudaMalloc(&csr->finish, sizeof(WorkItem) * fin.size()));
-    ALS_CUDA(cudaMemcpyAsync(csr->finish, fin.data(), sizeof(WorkItem) * fin.size(), cudaMemcpyHostToDevice,
-                             ctx->stream));
+    if ((rc = dev_alloc(ctx, (void **)&csr->finish, sizeof(WorkItem) * fin.size(), up)) != ALS_OK) return rc;
+    ALS_CUDA(cudaMemcpyAsync(csr->finish, fin.data(), sizeof(WorkItem) * fin.size(), cudaMemcpyHostToDevice, up));
   }
   if (!chunks.empty()) {
-    ALS_CUDA(cudaMalloc(&csr->chunks, sizeof(WorkItem) * chunks.size()));
-    ALS_CUDA(cudaMalloc(&csr->chunk_owner, sizeof(int32_t) * owner.size()));
-    ALS_CUDA(cudaMemcpyAsync(csr->chunks, chunks.data(), sizeof(WorkItem) * chunks.size(), cudaMemcpyHostToDevice,
-                             ctx->stream));
-    ALS_CUDA(cudaMemcpyAsync(csr->chunk_owner, owner.data(), sizeof(int32_t) * owner.size(), cudaMemcpyHostToDevice,
-                             ctx->stream));
+    if ((rc = dev_alloc(ctx, (void **)&csr->chunks, sizeof(WorkItem) * chunks.size(), up)) != ALS_OK) return rc;
+    if ((rc = dev_alloc(ctx, (void **)&csr->chunk_owner, sizeof(int32_t) * owner.size(), up)) != ALS_OK) return rc;
+    ALS_CUDA(cudaMemcpyAsync(csr->chunks, chunks.data(), sizeof(WorkItem) * chunks.size(), cudaMemcpyHostToDevice, up));
+    ALS_CUDA(cudaMemcpyAsync(csr->chunk_owner, owner.data(), sizeof(int32_t) * owner.size(), cudaMemcpyHostToDevice, up));
   }
-  ALS_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vectors die here
+  ALS_CUDA(cudaEventRecord(ctx->ev_join, up));
+  ALS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later kernels see the lists
+  ALS_CUDA(cudaStreamSynchronize(up));                          // the host vectors die here
   return ALS_OK;
 }
 
@@ -222,6 +242,13 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   ALS_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
   ALS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   ALS_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  ALS_CUDA(cudaEventCreateWithFlags(&ctx->sched_ev, cudaEventDisableTiming));
+  {
+    cudaMemPool_t pool;
+    ALS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;  // never hand freed blocks back to the driver while the context lives
+    ALS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   ALS_CUDA(cudaEventCreate(&ctx->ev0));
   ALS_CUDA(cudaEventCreate(&ctx->ev1));
   ALS_CUDA(cudaMalloc(&ctx->G, sizeof(float) * 256 * 256));
@@ -252,6 +279,12 @@ ALS_API int als_ctx_destroy(als_ctx *ctx) {
   cudaFree(ctx->dscalars);
   cudaFree(ctx->scratch);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->sched_pinned) cudaFreeHost(ctx->sched_pinned);
+  cudaEventDestroy(ctx->sched_ev);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -383,9 +416,13 @@ ALS_API int als_csr_upload(als_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz
       return ALS_E_INVALID;
     }
   }
-  ALS_CUDA(cudaMalloc(&c->indptr, sizeof(int32_t) * (rows + 1)));
-  ALS_CUDA(cudaMalloc(&c->indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
-  ALS_CUDA(cudaMalloc(&c->data, sizeof(float) * std::max<int64_t>(nnz, 1)));
+  int arc;
+  if ((arc = dev_alloc(ctx, (void **)&c->indptr, sizeof(int32_t) * (rows + 1))) != ALS_OK ||
+      (arc = dev_alloc(ctx, (void **)&c->indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1))) != ALS_OK ||
+      (arc = dev_alloc(ctx, (void **)&c->data, sizeof(float) * std::max<int64_t>(nnz, 1))) != ALS_OK) {
+    als_csr_destroy(c);
+    return arc;
+  }
   ALS_CUDA(cudaMemcpyAsync(c->indptr, ip, sizeof(int32_t) * (rows + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (nnz) {
     ALS_CUDA(cudaMemcpyAsync(c->indices, indices + base, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
@@ -474,19 +511,25 @@ ALS_API int als_csr_download(als_ctx *ctx, const als_csr *csr, int32_t *indptr, 
 
 ALS_API int als_csr_destroy(als_csr *csr) {
   if (!csr) return ALS_OK;
-  if (csr->ctx) {
-    cudaSetDevice(csr->ctx->device);
-    cudaStreamSynchronize(csr->ctx->stream);
+  als_ctx *ctx = csr->ctx;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    if (ctx->sched_owner == csr) {  // its indptr copy may still be in flight into the shared pinned buffer
+      cudaEventSynchronize(ctx->sched_ev);
+      ctx->sched_owner = nullptr;
+    }
+    // stream-ordered frees: everything queued so far on the compute stream (which every other stream is joined
+    // into before an entry point returns) still sees the arrays
+    if (csr->owns) {
+      dev_free(ctx, csr->indptr);
+      dev_free(ctx, csr->indices);
+      dev_free(ctx, csr->data);
+    }
+    dev_free(ctx, csr->work);
+    dev_free(ctx, csr->finish);
+    dev_free(ctx, csr->chunks);
+    dev_free(ctx, csr->chunk_owner);
   }
-  if (csr->owns) {
-    cudaFree(csr->indptr);
-    cudaFree(csr->indices);
-    cudaFree(csr->data);
-  }
-  cudaFree(csr->work);
-  cudaFree(csr->finish);
-  cudaFree(csr->chunks);
-  cudaFree(csr->chunk_owner);
   delete csr;
   return ALS_OK;
 }
@@ -504,7 +547,11 @@ ALS_API int als_factors_create(als_ctx *ctx, int64_t rows, int factors, als_fact
   f->f = factors;
   f->ld = round_up(factors, 16);
   const int64_t bytes = sizeof(float) * std::max<int64_t>(rows, 1) * f->ld;
-  ALS_CUDA(cudaMalloc(&f->d, bytes));
+  int arc = dev_alloc(ctx, (void **)&f->d, bytes);
+  if (arc != ALS_OK) {
+    delete f;
+    return arc;
+  }
   ALS_CUDA(cudaMemsetAsync(f->d, 0, bytes, ctx->stream));
   *out = f;
   return ALS_OK;
@@ -564,10 +611,22 @@ ALS_API int als_factors_shape(const als_factors *f, int64_t *rows, int *factors,
   return ALS_OK;
 }
 
-ALS_API int als_factors_ipc_export(als_ctx *ctx, const als_factors *f, void *handle) {
-  ALS_REQUIRE(ctx && f && handle, "als_factors_ipc_export: NULL argument");
+ALS_API int als_factors_ipc_export(als_ctx *ctx, const als_factors *cf, void *handle) {
+  ALS_REQUIRE(ctx && cf && handle, "als_factors_ipc_export: NULL argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == ALS_IPC_HANDLE_BYTES, "IPC handle size");
   ALS_CUDA(cudaSetDevice(ctx->device));
+  als_factors *f = const_cast<als_factors *>(cf);
+  if (f->pooled) {
+    // blocks of the stream-ordered pool cannot be exported with cudaIpcGetMemHandle: move the matrix (once)
+    const int64_t bytes = sizeof(float) * std::max<int64_t>(f->rows, 1) * f->ld;
+    float *moved = nullptr;
+    ALS_CUDA(cudaMalloc(&moved, bytes));
+    ALS_CUDA(cudaMemcpyAsync(moved, f->d, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    dev_free(ctx, f->d);
+    ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+    f->d = moved;
+    f->pooled = false;
+  }
   cudaIpcMemHandle_t h;
   ALS_CUDA(cudaIpcGetMemHandle(&h, f->d));
   memcpy(handle, &h, sizeof(h));
@@ -617,9 +676,13 @@ ALS_API int als_factors_destroy(als_factors *f) {
   if (f->ctx && (f->n_peers || !f->peer_maps.empty())) als_factors_ipc_detach(f->ctx, f);
   if (f->ctx) {
     cudaSetDevice(f->ctx->device);
-    cudaStreamSynchronize(f->ctx->stream);
+    if (f->pooled) {
+      dev_free(f->ctx, f->d);
+    } else {
+      cudaStreamSynchronize(f->ctx->stream);
+      cudaFree(f->d);
+    }
   }
-  cudaFree(f->d);
   delete f;
   return ALS_OK;
 }
@@ -633,7 +696,7 @@ static int check_half(const char *who, als_ctx *ctx, const als_csr *C, const als
               (long long)Y->rows);
   ALS_REQUIRE(C->row_offset + C->rows <= X->rows, "%s: C rows [%lld, %lld) exceed X's %lld rows", who,
               (long long)C->row_offset, (long long)(C->row_offset + C->rows), (long long)X->rows);
-  return ALS_OK;
+  return ensure_schedule(ctx, const_cast<als_csr *>(C));  // a device-transposed matrix sorts its rows at first use
 }
 
 ALS_API int als_gramian(als_ctx *ctx, const als_factors *Y, float *G_host) {

@@ -84,6 +84,11 @@ struct als_ctx {
   // pinned host staging
   void *pinned = nullptr;
   int64_t pinned_bytes = 0;
+  // a transposed CSR whose schedule has not been built yet (csr.cu): its indptr lands here, asynchronously
+  struct als_csr *sched_owner = nullptr;
+  int32_t *sched_pinned = nullptr;
+  int64_t sched_pinned_cap = 0;
+  cudaEvent_t sched_ev = nullptr;
   // per-kernel profiling (als_profile_*)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events[8];  // pairs (start, stop) per category
@@ -98,6 +103,7 @@ struct als_factors {
   int f = 0;   // logical factors
   int ld = 0;  // device row stride (multiple of 16, zero padded)
   float *d = nullptr;
+  bool pooled = true;  // d comes from the stream-ordered pool (moved to a cudaMalloc block when exported over IPC)
   // peer replicas of the same matrix on the other ranks (CUDA IPC mappings over NVLink): the solve kernels
   // mirror every row they write into these, which replaces the all-gather after a half-iteration
   float **peers_dev = nullptr;  // device array of n_peers base pointers (self excluded)
@@ -117,6 +123,7 @@ struct als_csr {
   int64_t n_work = 0;
   // work is sorted by length, so the items of at most 48 / 32 / 16 / 0 nonzeros are suffixes: first index of each
   int64_t le_begin[4] = {0, 0, 0, 0};
+  bool sched_pending = false;  // transposed on the device: the schedule is built at first use (ensure_schedule)
   als::WorkItem *finish = nullptr;  // finish pass: one per giant row (row, first slot, #slots)
   int64_t n_finish = 0;
   int64_t n_slots = 0;
@@ -141,6 +148,13 @@ enum {
   kCtrDeferredWork = 6, kCtrWhitenOk = 7, kCtrHasNan = 8
 };
 constexpr int kShortThresholds[4] = {48, 32, 16, 0};  // als_csr::le_begin[i] <-> length <= kShortThresholds[i]
+
+// Device memory comes from CUDA's stream-ordered pool on ctx->stream with the release threshold lifted, so the
+// arrays of a second fit() are served from what the first one freed (cudaMalloc / cudaFree cost 0.1-1 ms each and
+// cudaFree synchronises the device).  Factor matrices exported over CUDA IPC are the exception (api.cu).
+int dev_alloc(als_ctx *ctx, void **ptr, int64_t bytes, cudaStream_t stream = nullptr);  // nullptr: ctx->stream
+void dev_free(als_ctx *ctx, void *ptr);
+int ensure_schedule(als_ctx *ctx, als_csr *csr);
 
 int ensure_scratch(als_ctx *ctx, int64_t bytes);
 int ensure_device_buffer(als_ctx *ctx, void **buf, int64_t *cap, int64_t bytes);

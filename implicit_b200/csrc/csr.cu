@@ -66,22 +66,41 @@ int csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out) {
   t->rows = cols;
   t->cols = rows;
   t->nnz = nnz;
-  ALS_CUDA(cudaMalloc(&t->indptr, sizeof(int32_t) * ((int64_t)cols + 1)));
-  ALS_CUDA(cudaMalloc(&t->indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
-  ALS_CUDA(cudaMalloc(&t->data, sizeof(float) * std::max<int64_t>(nnz, 1)));
-  std::vector<int32_t> h_indptr((size_t)cols + 1, 0);
+  int rc;
+  if ((rc = dev_alloc(ctx, (void **)&t->indptr, sizeof(int32_t) * ((int64_t)cols + 1))) != ALS_OK ||
+      (rc = dev_alloc(ctx, (void **)&t->indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1))) != ALS_OK ||
+      (rc = dev_alloc(ctx, (void **)&t->data, sizeof(float) * std::max<int64_t>(nnz, 1))) != ALS_OK) {
+    als_csr_destroy(t);
+    return rc;
+  }
+  // one pinned landing buffer per context: a transposed matrix whose schedule is still pending owns it
+  if (ctx->sched_owner && (rc = ensure_schedule(ctx, ctx->sched_owner)) != ALS_OK) {
+    als_csr_destroy(t);
+    return rc;
+  }
+  const int64_t need = sizeof(int32_t) * ((int64_t)cols + 1);
+  if (need > ctx->sched_pinned_cap) {
+    if (ctx->sched_pinned) ALS_CUDA(cudaFreeHost(ctx->sched_pinned));
+    ctx->sched_pinned = nullptr;
+    ctx->sched_pinned_cap = 0;
+    ALS_CUDA(cudaMallocHost((void **)&ctx->sched_pinned, (size_t)need));
+    ctx->sched_pinned_cap = need;
+  }
   if (nnz > 0) {
     int32_t *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
-    ALS_CUDA(cudaMalloc(&keys_out, sizeof(int32_t) * nnz));
-    ALS_CUDA(cudaMalloc(&vals_in, sizeof(int32_t) * nnz));
-    ALS_CUDA(cudaMalloc(&vals_out, sizeof(int32_t) * nnz));
     int end_bit = 1;
     while (end_bit < 32 && (1ll << end_bit) < (long long)cols) ++end_bit;
     ALS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, in->indices, keys_out, vals_in, vals_out, (int)nnz, 0,
                                              end_bit, ctx->stream));
-    ALS_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    if ((rc = dev_alloc(ctx, (void **)&keys_out, sizeof(int32_t) * nnz)) != ALS_OK ||
+        (rc = dev_alloc(ctx, (void **)&vals_in, sizeof(int32_t) * nnz)) != ALS_OK ||
+        (rc = dev_alloc(ctx, (void **)&vals_out, sizeof(int32_t) * nnz)) != ALS_OK ||
+        (rc = dev_alloc(ctx, &tmp, (int64_t)tmp_bytes)) != ALS_OK) {
+      als_csr_destroy(t);
+      return rc;
+    }
     iota_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(vals_in, nnz);
     ALS_CUDA(cudaGetLastError());
     ALS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, in->indices, keys_out, vals_in, vals_out, (int)nnz, 0,
@@ -92,21 +111,20 @@ int csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out) {
     indptr_from_sorted_kernel<<<(cols + 1 + 255) / 256, 256, 0, ctx->stream>>>(keys_out, nnz, cols, t->indptr);
     ALS_CUDA(cudaGetLastError());
     ctx->launches += 3;
-    ALS_CUDA(cudaMemcpyAsync(h_indptr.data(), t->indptr, sizeof(int32_t) * ((size_t)cols + 1), cudaMemcpyDeviceToHost,
-                             ctx->stream));
-    ALS_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(keys_out);
-    cudaFree(vals_in);
-    cudaFree(vals_out);
-    cudaFree(tmp);
+    dev_free(ctx, keys_out);  // stream ordered: after the kernels above
+    dev_free(ctx, vals_in);
+    dev_free(ctx, vals_out);
+    dev_free(ctx, tmp);
   } else {
     ALS_CUDA(cudaMemsetAsync(t->indptr, 0, sizeof(int32_t) * ((int64_t)cols + 1), ctx->stream));
   }
-  int rc = build_schedule(ctx, t, h_indptr.data());
-  if (rc != ALS_OK) {
-    als_csr_destroy(t);
-    return rc;
-  }
+  // The schedule needs the row lengths on the host.  The copy is left in flight and the schedule is built at the
+  // first solve over this matrix (ensure_schedule): in a fit that is the item half, so the host-side sort of the
+  // rows overlaps the user half that is already running instead of leaving the GPU idle.
+  ALS_CUDA(cudaMemcpyAsync(ctx->sched_pinned, t->indptr, (size_t)need, cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(cudaEventRecord(ctx->sched_ev, ctx->stream));
+  t->sched_pending = true;
+  ctx->sched_owner = t;
   *out = t;
   return ALS_OK;
 }

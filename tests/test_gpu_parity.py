@@ -428,3 +428,46 @@ def test_shard_gramian_pregram_and_slices_match_plain_path(lib, ctx, orc):
                 np.testing.assert_array_equal(got.data, ref.data)
             S.close()
         np.testing.assert_array_equal(dX.download(), exp)
+
+
+# ---------------------------------------------------------------------------------------- short-row (n x n) path
+@pytest.mark.parametrize("f", [32, 40, 64])
+def test_cholesky_short_row_classes_and_deferrals(lib, ctx, orc, f):
+    """cholesky_short.cu: rows at every class boundary (1, 15, 16, 17, 31, 32, 33, 47, 48, 49 nonzeros ...), an
+    empty row, rows the path must hand back (|c| < 1, an explicit zero, a negative confidence below 1 in size)
+    and rows it keeps (negative confidences of size >= 1, c == 1 exactly), against the oracle."""
+    rng = np.random.default_rng(1000 + f)
+    items = 4000
+    lengths = [0, 1, 2, 7, 8, 9, 15, 16, 17, 24, 31, 32, 33, 40, 47, 48, 49, 63, 64, 65, 100] * 40
+    rows, cols, vals = [], [], []
+    for u, n in enumerate(lengths):
+        c = rng.choice(items, n, replace=False)
+        v = 1 + 4 * rng.random(n)
+        kind = u % 7
+        if n and kind == 1:
+            v[0] = 0.5          # weight |c| - 1 < 0: deferred to the full-size kernel
+        elif n and kind == 2:
+            v[0] = 0.0          # explicit zero: subtracts y y^T, deferred
+        elif n and kind == 3:
+            v[: n // 2 + 1] *= -1  # disliked with confidence >= 1: stays on the short path
+        elif n and kind == 4:
+            v[0] = 1.0          # weight exactly 0
+        elif n and kind == 5:
+            v[0] = -0.25        # deferred
+        rows += [u] * n
+        cols += c.tolist()
+        vals += v.tolist()
+    users = len(lengths)
+    Cui = sp.csr_matrix((np.array(vals, dtype=np.float32), (rows, cols)), shape=(users, items))
+    assert (Cui.data == 0).sum() > 0  # the explicit zeros are stored
+    Y = (rng.standard_normal((items, f)) * 0.2).astype(np.float32)
+    X = np.zeros((users, f), dtype=np.float32)
+    exp = X.copy()
+    orc.least_squares(Cui, exp, Y, 0.05)
+    got = _gpu_half(lib, ctx, Cui, X, Y, 0.05, use_cg=False)
+    e = row_err(got, exp)
+    lens = np.diff(Cui.indptr)
+    print(f"f={f}: max {e.max():.2e}; by class <=16 {e[lens <= 16].max():.2e}, <=32 {e[(lens > 16) & (lens <= 32)].max():.2e}, "
+          f"<=48 {e[(lens > 32) & (lens <= 48)].max():.2e}, longer {e[lens > 48].max():.2e}")
+    assert np.all(got[lens == 0] == 0)
+    assert e.max() < CHOL_MAX
