@@ -335,7 +335,7 @@ def run_ours(args):
         X0p[:], Y0p[:] = X0, Y0
         h2d = Cpin.data.nbytes + Cpin.indices.nbytes + Cpin.indptr.nbytes + X0.nbytes + Y0.nbytes
         d2h = X0.nbytes + Y0.nbytes
-        reps = max(2, min(5, args.steps))
+        reps = max(3, min(7, args.steps))
         times = []
         for rep in range(reps + 1):
             m = AlternatingLeastSquares(factors=f, regularization=reg, use_cg=use_cg, iterations=E2E_ITERS,
@@ -366,9 +366,13 @@ def run_ours(args):
             if rep > 0:  # first repetition is warm-up
                 times.append(pg.allreduce_max(dt) if world > 1 else dt)
             del m
-        e2e = {"value": (users + items) * E2E_ITERS / float(np.mean(times)), "unit": UNIT,
+        # Median over the repetitions: about one fit in five on the measurement boxes takes an extra ~100 ms in a
+        # host-side stall that moves from repetition to repetition (every fit is listed, and the mean alongside).
+        e2e = {"value": (users + items) * E2E_ITERS / float(np.median(times)), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "step": f"fit() of {E2E_ITERS} iterations", "s_per_fit": float(np.mean(times))}
+               "step": f"fit() of {E2E_ITERS} iterations, median of {len(times)} fits",
+               "s_per_fit": float(np.median(times)), "s_per_fit_mean": float(np.mean(times)),
+               "fits_ms": [round(1e3 * x, 2) for x in times]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
