@@ -41,9 +41,10 @@ def build_port(force=False):
 
 
 def build_ref(force=False):
-    from . import build_ref as _b
+    import importlib
 
-    return _b.build(force=force)
+    # not `from . import build_ref`: that name is this function once the package is initialised
+    return importlib.import_module(__name__ + ".build_ref").build(force=force)
 
 
 def have_ref():

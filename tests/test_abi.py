@@ -51,3 +51,15 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: compiles (or finds up to date) the library, the oracle port and, where the
+    reference is present, oracle/_ref -- and every header symbol resolves."""
+    import __graft_entry__ as entry
+
+    assert entry.build() is None
+    import oracle
+
+    if os.path.isdir("/root/reference"):
+        assert oracle.have_ref() and oracle.have_ref_evaluation()
