@@ -547,10 +547,20 @@ ALS_API int als_factors_create(als_ctx *ctx, int64_t rows, int factors, als_fact
   f->f = factors;
   f->ld = round_up(factors, 16);
   const int64_t bytes = sizeof(float) * std::max<int64_t>(rows, 1) * f->ld;
-  int arc = dev_alloc(ctx, (void **)&f->d, bytes);
-  if (arc != ALS_OK) {
-    delete f;
-    return arc;
+  // with a communicator the matrix will be exported over IPC (multi-GPU fit): take a cudaMalloc block right away
+  f->pooled = ctx->world == 1;
+  if (f->pooled) {
+    int arc = dev_alloc(ctx, (void **)&f->d, bytes);
+    if (arc != ALS_OK) {
+      delete f;
+      return arc;
+    }
+  } else {
+    cudaError_t e = cudaMalloc(&f->d, bytes);
+    if (e != cudaSuccess) {
+      delete f;
+      return cuda_fail(e, "cudaMalloc (factor matrix)", __FILE__, __LINE__);
+    }
   }
   ALS_CUDA(cudaMemsetAsync(f->d, 0, bytes, ctx->stream));
   *out = f;
