@@ -7,7 +7,10 @@ the user's withheld items in a scalar loop.  Here the batches are sized for the 
 launch covers ``BATCH`` users) and the per-user bookkeeping is whole-batch array arithmetic on the
 returned ``(users, K)`` id matrix; the four sums are the same quantities, accumulated in float64.
 
-``leave_k_out_split`` (:141-233) is dataset preparation, not a caller of the hot path, and is out of scope.
+``leave_k_out_split`` (:141-233) is dataset preparation rather than a caller of the hot path; it is provided with the
+reference's contract (every eligible user leaves exactly K entries in the test matrix, train + test == input, a
+reserved share of users stays train-only, the same ValueErrors).  The reference draws its shuffle from numpy's
+global generator there (:128), so the split itself is seeded here and is not bit-comparable.
 """
 import numpy as np
 from scipy.sparse import csr_matrix
@@ -34,6 +37,39 @@ def train_test_split(ratings, train_percentage=0.8, random_state=None):
     train, test = parts
     test.data[test.data < 0] = 0
     test.eliminate_zeros()
+    return train, test
+
+
+def leave_k_out_split(ratings, K=1, train_only_size=0.0, random_state=None):
+    """'Leave K out': every eligible user (more than K + 1 stored entries, evaluation.pyx:191) gives K randomly
+    chosen entries to the test matrix; `train_only_size` is the fraction of users kept out of the test set
+    (:194-198).  Returns (train, test) CSR matrices of the input's shape with train + test == ratings."""
+    if K < 1:
+        raise ValueError("The 'K' must be >= 1.")
+    if not 0.0 <= train_only_size < 1.0:
+        raise ValueError("The 'train_only_size' must be in the range (0.0 <= x < 1.0).")
+    ratings = ratings.tocoo()
+    rng = check_random_state(random_state)
+    users, items, data = ratings.row, ratings.col, ratings.data
+    unique_users, counts = np.unique(users, return_counts=True)
+    candidate = counts > K + 1
+    if train_only_size > 0.0:
+        size = max(1, int(len(unique_users) * train_only_size))  # _choose, :73-75
+        reserved = rng.choice(len(unique_users), size=size, replace=False)
+        # positions (not ids) drawn from range(len(unique_users)) are matched against the ids, as in :195-197
+        candidate &= ~np.isin(unique_users, reserved)
+    in_candidates = np.isin(users, unique_users[candidate])
+    # K random entries per candidate user: shuffle the entries, stable-sort by user, take the first K of each run
+    pos = np.flatnonzero(in_candidates)
+    pos = pos[rng.permutation(len(pos))]
+    pos = pos[np.argsort(users[pos], kind="stable")]
+    run_start = np.flatnonzero(np.r_[True, users[pos][1:] != users[pos][:-1]]) if len(pos) else np.zeros(0, dtype=int)
+    rank_in_run = np.arange(len(pos)) - np.repeat(run_start, np.diff(np.r_[run_start, len(pos)]))
+    test_pos = pos[rank_in_run < K]
+    is_test = np.zeros(len(users), dtype=bool)
+    is_test[test_pos] = True
+    test = csr_matrix((data[is_test], (users[is_test], items[is_test])), shape=ratings.shape, dtype=ratings.dtype)
+    train = csr_matrix((data[~is_test], (users[~is_test], items[~is_test])), shape=ratings.shape, dtype=ratings.dtype)
     return train, test
 
 

@@ -73,6 +73,47 @@ def test_train_test_split_matches_golden(name):
     assert (tr != tr2).nnz == 0
 
 
+# ---- leave_k_out_split: the reference's own property tests (tests/evaluation_test.py:30-100)
+def _ratings():
+    import scipy.sparse as sp
+
+    return sp.random(100, 100, density=0.5, format="csr", dtype=np.float32, random_state=5).tocoo()
+
+
+@pytest.mark.parametrize("K", [1, 3])
+def test_leave_k_out_split_contract(K):
+    from implicit_b200 import evaluation
+
+    mat = _ratings()
+    train, test = evaluation.leave_k_out_split(mat, K=K, random_state=1)
+    assert train.shape == mat.shape and test.shape == mat.shape          # :30-38
+    assert ((train + test) - mat).nnz == 0                                # :41-49
+    assert mat.sum() > 0 and test.sum() > 0 and train.sum() > 0          # :52-66
+    counts = np.bincount(mat.row, minlength=100)
+    held = np.diff(test.indptr)
+    assert np.all(held[counts > K + 1] == K) and np.all(held[counts <= K + 1] == 0)
+    t2, _ = evaluation.leave_k_out_split(mat, K=K, random_state=1)       # seeded
+    assert (t2 != train).nnz == 0
+    if oracle.have_ref_evaluation():  # same contract from the reference's compiled module
+        rt, rs = oracle.ref_evaluation().leave_k_out_split(mat, K=K)
+        assert ((rt + rs) - mat).nnz == 0 and np.array_equal(np.diff(rs.indptr), held)
+
+
+def test_leave_k_out_split_train_only_and_errors():
+    from implicit_b200 import evaluation
+
+    mat = _ratings()
+    train, test = evaluation.leave_k_out_split(mat, K=1, train_only_size=0.8, random_state=2)
+    train_only = ~np.isin(np.unique(train.tocoo().row), test.tocoo().row)
+    assert train_only.sum() == int(train.shape[0] * 0.8)                  # :69-76
+    with pytest.raises(ValueError):
+        evaluation.leave_k_out_split(None, K=0)                           # :79-84
+    with pytest.raises(ValueError):
+        evaluation.leave_k_out_split(None, K=1, train_only_size=-1.0)     # :87-92
+    with pytest.raises(ValueError):
+        evaluation.leave_k_out_split(None, K=1, train_only_size=1.0)      # :95-100
+
+
 @pytest.mark.gpu
 def test_evaluate_fitted_model_against_oracle_ids():
     """The model's own recommend() under ranking_metrics_at_k == the scalar restatement fed by the same
