@@ -84,7 +84,8 @@ int als_host_free(void *ptr);
  * Replaces CSRMatrix::CSRMatrix(rows, cols, nonzeros, indptr, indices, data), implicit/gpu/matrix.cu:222-251. */
 int als_csr_upload(als_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz, const int32_t *indptr,
                    const int32_t *indices, const float *data, int64_t row_offset, als_csr **out);
-/* Device transpose: out = in^T as CSR (replaces the host `Cui.T.tocsr()`, implicit/cpu/als.py:137). */
+/* Device transpose: out = in^T as CSR (replaces the host `Cui.T.tocsr()`, implicit/cpu/als.py:137).
+ * Asynchronous: the launch schedule of `out` is built at the first solve that uses it. */
 int als_csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out);
 /* A view of rows [r0, r1) of `in` as a shard (row_offset = r0) with its own schedule; shares the
  * parent's device arrays, so the parent must outlive it.  (No reference equivalent: multi-GPU sharding.) */
