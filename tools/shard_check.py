@@ -3,7 +3,6 @@ item half over rows [0, I/8), with ALS_B200_SHORT_MAX = 0 and 48 (the whitening 
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np
 from implicit_b200 import _lib, synthetic
 parts = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 ctx = _lib.Context(0)
