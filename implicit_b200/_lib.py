@@ -55,10 +55,12 @@ SIGNATURES = {
     "als_factors_shape": (c_int, [c_void_p, P(c_i64), P(c_int), P(c_int)]),
     "als_factors_has_nan": (c_int, [c_void_p, c_void_p, P(c_int)]),
     "als_factors_destroy": (c_int, [c_void_p]),
+    "als_ctx_set_knob": (c_int, [c_void_p, ctypes.c_char_p, c_int]),
     "als_gramian": (c_int, [c_void_p, c_void_p, c_void_p]),
     "als_least_squares": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
     "als_least_squares_with_gramian": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
     "als_gramian_shard": (c_int, [c_void_p, c_void_p, c_i64, c_i64]),
+    "als_whitened_factors": (c_int, [c_void_p, c_void_p, c_f64, c_void_p, c_void_p]),
     "als_least_squares_pregram": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
     "als_least_squares_cg_pregram": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_int]),
     "als_least_squares_cg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_int]),
@@ -156,6 +158,10 @@ class Context:
 
     def sync(self):
         check(self.lib.als_sync(self.h))
+
+    def set_knob(self, name, value):
+        """Measurement knobs (short_max, short_serial, whiten_fma, gramian_mma, cg_nv); see include/als_b200.h."""
+        check(self.lib.als_ctx_set_knob(self.h, name.encode(), int(value)))
 
     def info(self):
         name = ctypes.create_string_buffer(256)
@@ -400,6 +406,14 @@ def least_squares(ctx, Cui, X, Y, regularization):
     if rc == ALS_E_NOT_POSDEF:
         raise ValueError("cholesky failed on row %i. Try increasing the regularization parameter." % bad.value)
     check(rc)
+
+
+def whitened_factors(ctx, Y, regularization):
+    """(W, Z) of the short-row path: W = Y P (P = R^-1, Y^T Y + reg I = R^T R) and Z = Y (Y^T Y + reg I)^-1."""
+    W = np.empty((Y.rows, Y.factors), dtype=np.float32)
+    Z = np.empty((Y.rows, Y.factors), dtype=np.float32)
+    check(ctx.lib.als_whitened_factors(ctx.h, Y.h, float(regularization), ptr(W), ptr(Z)))
+    return W, Z
 
 
 def gramian_shard(ctx, Y, row0, nrows):

@@ -1,6 +1,7 @@
 // C-ABI entry points, device containers and the launch schedule (host side of libals_b200.so).
 #include <limits.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -233,6 +234,21 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   }
   als_ctx *ctx = new als_ctx();
   ctx->device = device;
+  {
+    struct { const char *env; const char *name; } table[] = {
+        {"ALS_B200_SHORT_MAX", "short_max"}, {"ALS_B200_SHORT_SERIAL", "short_serial"}, {"ALS_B200_WHITEN_FMA", "whiten_fma"},
+        {"ALS_B200_GRAMIAN_MMA", "gramian_mma"}, {"ALS_B200_CG_NV", "cg_nv"}};
+    for (const auto &t : table) {
+      const char *e = getenv(t.env);
+      if (!e) continue;
+      const int v = *e ? atoi(e) : 1;
+      if (als_ctx_set_knob(ctx, t.name, v) != ALS_OK) {
+        delete ctx;
+        return ALS_E_INVALID;
+      }
+      fprintf(stderr, "libals_b200: %s=%s is set (knob %s = %d)\n", t.env, e, t.name, v);
+    }
+  }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->l2_bytes = prop.l2CacheSize;
   ctx->mem_bytes = (int64_t)prop.totalGlobalMem;
@@ -254,10 +270,28 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   ALS_CUDA(cudaMalloc(&ctx->G, sizeof(float) * 256 * 256));
   ALS_CUDA(cudaMalloc(&ctx->Greg, sizeof(float) * 256 * 256));
   ALS_CUDA(cudaMalloc(&ctx->Pinv, sizeof(float) * 64 * 64));
+  ALS_CUDA(cudaMalloc(&ctx->Ginv, sizeof(float) * 64 * 64));
   ALS_CUDA(cudaMalloc(&ctx->counters, sizeof(int32_t) * 16));
   ALS_CUDA(cudaMalloc(&ctx->bad_row, sizeof(long long) * 2));
   ALS_CUDA(cudaMalloc(&ctx->dscalars, sizeof(double) * 8));
   *out = ctx;
+  return ALS_OK;
+}
+
+ALS_API int als_ctx_set_knob(als_ctx *ctx, const char *name, int value) {
+  ALS_REQUIRE(ctx && name, "als_ctx_set_knob: NULL argument");
+  als_knobs &k = ctx->knobs;
+  if (!strcmp(name, "short_max")) k.short_max = value >= 48 ? 48 : value >= 32 ? 32 : value >= 16 ? 16 : 0;
+  else if (!strcmp(name, "short_serial")) k.short_serial = value != 0;
+  else if (!strcmp(name, "whiten_fma")) k.whiten_fma = value != 0;
+  else if (!strcmp(name, "gramian_mma")) k.gramian_mma = value != 0;
+  else if (!strcmp(name, "cg_nv")) {
+    ALS_REQUIRE(value == 1 || value == 2 || value == 4, "als_ctx_set_knob: cg_nv must be 1, 2 or 4");
+    k.cg_nv = value;
+  } else {
+    set_error("als_ctx_set_knob: unknown knob '%s'", name);
+    return ALS_E_INVALID;
+  }
   return ALS_OK;
 }
 
@@ -272,7 +306,10 @@ ALS_API int als_ctx_destroy(als_ctx *ctx) {
   cudaFree(ctx->Greg);
   cudaFree(ctx->gram_partials);
   cudaFree(ctx->Pinv);
+  cudaFree(ctx->Ginv);
   cudaFree(ctx->whitened);
+  cudaFree(ctx->zfactors);
+  cudaFree(ctx->dense_bt);
   cudaFree(ctx->deferred);
   cudaFree(ctx->counters);
   cudaFree(ctx->bad_row);
@@ -749,6 +786,37 @@ ALS_API int als_least_squares(als_ctx *ctx, const als_csr *C, als_factors *X, co
   rc = launch_gramian(ctx, Y);
   if (rc != ALS_OK) return rc;
   return finish_cholesky(ctx, C, X, Y, regularization, bad_row);
+}
+
+// W = Y (2^14 P) / 2^14 and Z = Y G^-1 of the short-row path, downloaded (tests and tools: the tcgen05 apply of
+// dense.cu against an fp64 product).  Leaves the Gramian of Y in the context like als_gramian.
+ALS_API int als_whitened_factors(als_ctx *ctx, const als_factors *Y, double regularization, float *W_host, float *Z_host) {
+  ALS_REQUIRE(ctx && Y && W_host && Z_host, "als_whitened_factors: NULL argument");
+  ALS_REQUIRE(Y->ld >= 32 && Y->ld <= 64, "als_whitened_factors: the short-row path covers 32..64 padded factors, got %d", Y->ld);
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  int rc = launch_gramian(ctx, Y);
+  if (rc != ALS_OK) return rc;
+  rc = launch_regularize(ctx, Y->f, Y->ld, (float)regularization);
+  if (rc != ALS_OK) return rc;
+  rc = short_rows_prepare(ctx, Y, ctx->stream);
+  if (rc != ALS_OK) return rc;
+  int32_t ok = 0;
+  ALS_CUDA(cudaMemcpyAsync(&ok, ctx->counters + kCtrWhitenOk, sizeof(ok), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<float> tmp((size_t)Y->rows * Y->ld);
+  for (int which = 0; which < 2; ++which) {
+    ALS_CUDA(cudaMemcpyAsync(tmp.data(), which ? ctx->zfactors : ctx->whitened, sizeof(float) * tmp.size(),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+    float *dst = which ? Z_host : W_host;
+    const float scale = which ? 1.f : 1.f / 16384.f;
+    for (int64_t r = 0; r < Y->rows; ++r)
+      for (int j = 0; j < Y->f; ++j) dst[r * Y->f + j] = tmp[(size_t)r * Y->ld + j] * scale;
+  }
+  if (!ok) {
+    set_error("als_whitened_factors: Y^T Y + reg I is not positive definite");
+    return ALS_E_NOT_POSDEF;
+  }
+  return ALS_OK;
 }
 
 ALS_API int als_gramian_shard(als_ctx *ctx, const als_factors *Y, int64_t row0, int64_t nrows) {

@@ -389,14 +389,9 @@ int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors 
     set_error("cg: X and Y strides differ (%d vs %d)", X->ld, Y->ld);
     return ALS_E_INVALID;
   }
-  // float4 words per lane: 1 keeps the per-row overhead (symv + cross-group reductions) lowest, which wins
-  // on short rows; ALS_B200_CG_NV overrides for experiments
-  static int nv_env = -1;
-  if (nv_env < 0) {
-    const char *e = getenv("ALS_B200_CG_NV");
-    nv_env = e ? atoi(e) : 0;
-  }
-  const int nv = nv_env ? nv_env : 2;  // measured on B200: C2 (f=64) 6.0 ms/iter at 2 vs 6.6 (1) and 9.3 (4); C3 (f=128) 9.9 vs 11.2 and 11.9
+  // float4 words per lane (knob cg_nv): measured on B200: C2 (f=64) 6.0 ms/iter at 2 vs 6.6 (1) and 9.3 (4);
+  // C3 (f=128) 9.9 vs 11.2 and 11.9
+  const int nv = ctx->knobs.cg_nv;
 #define ALS_CG_CASE(FF)                                                   \
   case FF / 16:                                                           \
     if (nv == 4) return run_cg<FF, 4>(ctx, C, X, Y, cg_steps);            \

@@ -30,7 +30,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3)
 cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
                      float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
                      const WorkItem *__restrict__ work, int n_work, const int32_t *n_work_dev, int32_t *counter,
-                     float *slots, long long *bad_row, int pass, int dbg, float *const *peers, int n_peers) {
+                     float *slots, long long *bad_row, int pass, int dbg_arg, float *const *peers, int n_peers) {
+#ifdef ALS_B200_ABLATE
+  const int dbg = dbg_arg;
+#else
+  constexpr int dbg = 0;
+  (void)dbg_arg;
+#endif
   using C = Cfg<NB>;
   constexpr int F = C::F;
   if (n_work_dev) n_work = *n_work_dev;  // a list built on the device (items deferred by the short-row kernels)
@@ -181,23 +187,20 @@ __global__ void init_solver_scalars(int32_t *counters, long long *bad_row) {
   if (threadIdx.x == 0) bad_row[0] = LLONG_MAX;
 }
 
-// Timing ablations (results are WRONG when set): ALS_B200_DEBUG bit0 skip back-substitution, bit1 skip pivot
-// elimination, bit2 skip trailing updates, bit3 skip the whole factorisation.  Never set in production.
+// Timing ablations (tools/ablate.py) exist only in builds with -DALS_B200_ABLATE: ALS_B200_DEBUG bit0 skips the back
+// substitution, bit1 the pivot elimination, bit2 the trailing updates, bit3 the whole factorisation (results are
+// WRONG when set).  A release build compiles the flag to 0 and the branches away.
 static int debug_flags() {
+#ifdef ALS_B200_ABLATE
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("ALS_B200_DEBUG");
     v = e ? atoi(e) : 0;
   }
   return v;
-}
-
-// Longest row (in nonzeros) the short-row path takes: 48 by default; ALS_B200_SHORT_MAX = 0 / 16 / 32 / 48
-// overrides it (0 disables the path; a measurement knob, results agree to fp32 rounding either way).
-static int short_row_limit() {
-  const char *e = getenv("ALS_B200_SHORT_MAX");  // read per call: tools/short_check.py flips it within a process
-  const int want = e ? atoi(e) : 48;
-  return want >= 48 ? 48 : want >= 32 ? 32 : want >= 16 ? 16 : 0;
+#else
+  return 0;
+#endif
 }
 
 template <int NB>
@@ -224,7 +227,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
   ctx->launches++;
   // Items of at most `short_max` nonzeros (a suffix of the length-sorted work list) go through the n x n
   // push-through system of cholesky_short.cu when there are enough of them to pay for whitening Y.
-  int short_max = std::min(short_row_limit(), 16 * (NB - 1));
+  int short_max = std::min(ctx->knobs.short_max, 16 * (NB - 1));
   int64_t n_main = Cm->n_work;
   if (short_max > 0) {
     const int64_t begin = Cm->le_begin[short_max > 32 ? 0 : short_max > 16 ? 1 : 2];
@@ -239,7 +242,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
     // The short-row side (whitening, the short-row kernels, the second pass of the full-size kernel over what they
     // hand back) runs on the aux stream.  The single-CTA factorisation of G is launched first and hides behind the
     // full-size kernel; the rest moves in as that kernel's persistent CTAs run out of long rows.
-    const bool overlap = short_max > 0 && n_main > 0 && getenv("ALS_B200_SHORT_SERIAL") == nullptr;
+    const bool overlap = short_max > 0 && n_main > 0 && !ctx->knobs.short_serial;
     cudaStream_t side = overlap ? ctx->aux : ctx->stream;
     if (short_max > 0) {
       if (overlap) {

@@ -2,37 +2,54 @@
 // row with n nonzeros, n well below the factor count F, through the n x n "push-through" system instead of the
 // F x F normal equations.
 //
-// With G = Y^T Y + lambda I = R^T R (shared by every row of the half), P = R^-1 and the whitened factors W = Y P:
+// With G = Y^T Y + lambda I = R^T R (shared by every row of the half), P = R^-1, the whitened factors W = Y P and
+// the "solved" factors Z = Y G^-1 = W P^T:
 //     A_u = G + V^T D V,  b_u = V^T c+          V = the n gathered rows of Y,  D = diag(|c| - 1),  c+ = max(c, 0)
 //     x_u = A_u^-1 b_u = G^-1 V^T (I + D K)^-1 c+,   K = V G^-1 V^T = W_u W_u^T
-//         = P W_u^T E (I + E K E)^-1 E^-1 c+,        E = sqrt(D)
-// so a row costs an n x n Gram matrix of whitened rows (mma.sync 3xTF32, as in cholesky.cu with the roles of
-// "nonzero" and "factor" swapped), an n x n Cholesky of M = I + E K E (eigenvalues >= 1: always well conditioned),
-// one pass r = W_u^T (E s) and the product x = P r with the triangular P held in shared memory.  Rows with n <= 16
-// / 32 / 48 use a 16 / 32 / 48-wide system; cost drops from O(n F^2 + F^3) to O(n^2 F + n^3 + F^2).
-// fp32 accuracy is on par with the F x F path (DESIGN.md section 4.1b has the comparison against an fp64 solve).
+//         = Z_u^T E (I + E K E)^-1 E^-1 c+,          E = sqrt(D)
+// so a row costs an n x n Gram matrix of whitened rows (mma.sync, fp16 hi/lo split: three m16n8k16 products give
+// fp32-faithful K), an n x n LDL^T solve of M = I + E K E (eigenvalues >= 1: always well conditioned) and one
+// pass x = sum_i t_i z_i over the gathered rows of Z.  Cost drops from O(n F^2 + F^3) to O(n^2 F + n^3 + n F).
+//
+// Organisation (round 2): a warp takes a BATCH of 32 / G consecutive work items (the list is sorted by length) and
+//   A  forms the systems one row at a time, all 32 lanes on one row (cp.async gathers of W, pipelined across the
+//      rows of the batch; tensor-core Gram matrix), leaving M and the right-hand sides in shared memory;
+//   B  solves all systems of the batch AT ONCE, G lanes per system, the upper triangle of each M distributed by
+//      columns over the G lanes and held in registers: an elimination step costs one shuffle per multiplier for
+//      32 / G systems (the round-1 kernel spent a whole warp on one system: ~5x the instructions per row);
+//   C  gathers the rows of Z one row at a time and writes x (and its peer replicas) straight from registers.
 //
 // Not every short item qualifies: a negative weight |c| - 1 < 0 (|c| < 1, or an explicit zero) makes M indefinite,
 // chunks of giant rows are not rows, and a G that is not positive definite has no R.  Such items are appended to
 // a deferred list that the full-size kernel of cholesky.cu processes right after; results never depend on which
 // path took a row beyond fp32 rounding.
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "cholesky_device.cuh"
 
 namespace als {
 
 namespace {
 
-constexpr int kShortWarps = 8;
+// W is stored scaled by 2^14 (|W_ij| <= 1 because W^T W = I - lambda P^T P, so the scaled entries stay inside
+// the fp16 range and the hi / lo halves of everything above 2^-17 of the maximum keep 22 bits): the scale is
+// folded into P by whiten_factor_kernel and taken out again, exactly, when M and t are formed.
+constexpr float kWScale = 16384.f, kWScaleInv = 1.f / 16384.f;
 
-// ---- P = R^-1 in fp64 ---------------------------------------------------------------------------
+// ---- P = R^-1 and G^-1 = P P^T in fp64 ----------------------------------------------------------
 // One CTA of 32 x 32 threads on the augmented matrix [G | I] (F x 2F doubles in shared memory).  Gaussian
 // elimination without pivoting (G is SPD) turns it into [D U | L1^-1] with G = U^T D U, U unit upper triangular,
 // L1 = U^T; then R = D^1/2 U and P = R^-1 = (D^-1/2 L1^-1)^T.  One barrier per pivot: step k only reads row k.
-__global__ void __launch_bounds__(1024) whiten_factor_kernel(const float *__restrict__ Greg, int F, float *__restrict__ P,
-                                                             int32_t *ok) {
+// Outputs: Ps = 2^14 P (upper triangular) and Ginv = P P^T, both rounded to fp32 once.
+__global__ void __launch_bounds__(1024) whiten_factor_kernel(const float *__restrict__ Greg, int F, float *__restrict__ Ps,
+                                                             float *__restrict__ Ginv, int32_t *ok) {
   extern __shared__ __align__(16) unsigned char whiten_smem[];
   double *a = reinterpret_cast<double *>(whiten_smem);  // [F][2F + 1]
   const int ld = 2 * F + 1;
+  double *Pd = a + F * ld;                              // [F][F + 1]: P in double
+  const int ldp = F + 1;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < F; i += 32)
     for (int j = tx; j < 2 * F; j += 32) a[i * ld + j] = j < F ? (double)Greg[i * F + j] : (j - F == i ? 1.0 : 0.0);
@@ -59,12 +76,23 @@ __global__ void __launch_bounds__(1024) whiten_factor_kernel(const float *__rest
     double s = (double)rsqrtf((float)d);
     s = s * (1.5 - 0.5 * d * s * s);
     s = s * (1.5 - 0.5 * d * s * s);
-    for (int i = tx; i < F; i += 32) P[i * F + j] = i <= j ? (float)(a[j * ld + F + i] * s) : 0.f;
+    for (int i = tx; i < F; i += 32) {
+      const double p = i <= j ? a[j * ld + F + i] * s : 0.0;
+      Pd[i * ldp + j] = p;
+      Ps[i * F + j] = (float)(p * (double)kWScale);
+    }
   }
+  __syncthreads();
+  for (int i = ty; i < F; i += 32)
+    for (int j = tx; j < F; j += 32) {
+      double acc = 0.0;
+      for (int k = (i > j ? i : j); k < F; ++k) acc += Pd[i * ldp + k] * Pd[j * ldp + k];
+      Ginv[i * F + j] = (float)acc;
+    }
   if (threadIdx.x == 0) *ok = 1;
 }
 
-// ---- W = Y P ------------------------------------------------------------------------------------
+// ---- W = Y P (P upper triangular) and Z = Y G^-1 (full) ------------------------------------------
 // 128 rows per CTA pass; thread (ty, tx) owns rows 4 ty .. 4 ty + 3 and, in every 32-column half, columns
 // 4 tx .. 4 tx + 3 (so both the P reads and the W writes of a warp are contiguous and conflict free).
 template <int NB>
@@ -74,7 +102,7 @@ struct WhitenCfg {
   static constexpr int SMEM_FLOATS = F * F + RT * LDY;
 };
 
-template <int NB>
+template <int NB, bool TRI>
 __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restrict__ Y, const float *__restrict__ P,
                                                           float *__restrict__ W, int64_t rows) {
   using C = WhitenCfg<NB>;
@@ -99,7 +127,7 @@ __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restric
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int h = 0; h < NH; ++h) acc[i][h][0] = acc[i][h][1] = acc[i][h][2] = acc[i][h][3] = 0.f;
-    // P is upper triangular: row k only reaches the 32-column halves h >= k / 32
+    // an upper triangular P: row k only reaches the 32-column halves h >= k / 32
 #pragma unroll
     for (int kb = 0; kb < NH; ++kb) {
 #pragma unroll 4
@@ -109,14 +137,14 @@ __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restric
 #pragma unroll
         for (int i = 0; i < 4; ++i) y[i] = Ys[(4 * ty + i) * LDY + k];
 #pragma unroll
-        for (int h = kb; h < NH; ++h) {
+        for (int h = (TRI ? kb : 0); h < NH; ++h) {
           const int c = 32 * h + 4 * tx;
           p[h] = c < F ? *reinterpret_cast<const float4 *>(Ps + k * F + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int h = kb; h < NH; ++h) {
+          for (int h = (TRI ? kb : 0); h < NH; ++h) {
             acc[i][h][0] = fmaf(y[i], p[h].x, acc[i][h][0]);
             acc[i][h][1] = fmaf(y[i], p[h].y, acc[i][h][1]);
             acc[i][h][2] = fmaf(y[i], p[h].z, acc[i][h][2]);
@@ -139,363 +167,386 @@ __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restric
   }
 }
 
-// ---- W = Y P on the tensor cores ------------------------------------------------------------------
-// Warp per 16-row tile: A = the tile of Y (cp.async, double buffered), B = P pre-split into TF32 hi / lo parts in
-// shared memory, 3xTF32 mma.sync, triangular P: k-step s only reaches the 8-column tiles j >= s.  Memory-bound.
-constexpr int kWhitenWarps = 8;
-
-template <int NB>
-struct WhitenMmaCfg {
-  static constexpr int F = 16 * NB, NT8 = 2 * NB;
-  static constexpr int LDY = F + 4;   // A-fragment reads conflict free
-  static constexpr int LDP = F + 8;   // B-fragment reads conflict free
-  static constexpr int TILE = 16 * LDY;
-  static constexpr int SMEM_FLOATS = 2 * F * LDP + kWhitenWarps * 2 * TILE;
-};
-
-template <int NB>
-__global__ void __launch_bounds__(32 * kWhitenWarps, 2)
-whiten_rows_mma_kernel(const float *__restrict__ Y, const float *__restrict__ P, float *__restrict__ W, int64_t rows) {
-  using C = WhitenMmaCfg<NB>;
-  constexpr int F = C::F, NT8 = C::NT8, LDY = C::LDY, LDP = C::LDP;
-  extern __shared__ __align__(16) unsigned char whiten_mma_smem[];
-  uint32_t *Ph = reinterpret_cast<uint32_t *>(whiten_mma_smem);
-  uint32_t *Pl = Ph + F * LDP;
-  float *tiles = reinterpret_cast<float *>(Pl + F * LDP);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  for (int e = threadIdx.x; e < F * F; e += blockDim.x) {
-    uint32_t hi, lo;
-    split_tf32(__ldg(P + e), hi, lo);
-    Ph[(e / F) * LDP + e % F] = hi;
-    Pl[(e / F) * LDP + e % F] = lo;
-  }
-  __syncthreads();
-  float *mine = tiles + warp * 2 * C::TILE;
-  const int64_t ntiles = (rows + 15) >> 4;
-  const int64_t stride = (int64_t)gridDim.x * kWhitenWarps;
-  auto issue = [&](int64_t tile, int buf) {
-    if (tile < ntiles) {
-      float *st = mine + buf * C::TILE;
-      constexpr int CH = F / 4;
-#pragma unroll
-      for (int q = 0; q < 2 * NB; ++q) {  // 16 rows x F/4 chunks = 64 NB chunks
-        const int id = q * 32 + lane, row = id / CH, ch = id % CH;
-        int64_t r = tile * 16 + row;
-        if (r >= rows) r = rows - 1;  // clamp: the duplicate rows are never stored
-        cp_async16(st + row * LDY + ch * 4, Y + r * F + ch * 4);
-      }
-    }
-    cp_async_commit();
-  };
-  int64_t tile = (int64_t)blockIdx.x * kWhitenWarps + warp;
-  issue(tile, 0);
-  int buf = 0;
-  for (; tile < ntiles; tile += stride) {
-    issue(tile + stride, buf ^ 1);
-    cp_async_wait<1>();
-    __syncwarp();
-    const float *st = mine + buf * C::TILE;
-    float acc[NT8][4];
-#pragma unroll
-    for (int j = 0; j < NT8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll
-    for (int s = 0; s < NT8; ++s) {  // k-step: factor dimensions 8s .. 8s+7
-      uint32_t ah[4], al[4];
-      split_tf32(st[g * LDY + 8 * s + t], ah[0], al[0]);
-      split_tf32(st[(g + 8) * LDY + 8 * s + t], ah[1], al[1]);
-      split_tf32(st[g * LDY + 8 * s + t + 4], ah[2], al[2]);
-      split_tf32(st[(g + 8) * LDY + 8 * s + t + 4], ah[3], al[3]);
-#pragma unroll
-      for (int j = s; j < NT8; ++j) {
-        const uint32_t bh0 = Ph[(8 * s + t) * LDP + 8 * j + g], bh1 = Ph[(8 * s + t + 4) * LDP + 8 * j + g];
-        const uint32_t bl0 = Pl[(8 * s + t) * LDP + 8 * j + g], bl1 = Pl[(8 * s + t + 4) * LDP + 8 * j + g];
-        mma_tf32(acc[j], al[0], al[1], al[2], al[3], bh0, bh1);
-        mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
-        mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
-      }
-    }
-    const int64_t r0 = tile * 16 + g, r1 = r0 + 8;
-#pragma unroll
-    for (int j = 0; j < NT8; ++j) {
-      if (r0 < rows) *reinterpret_cast<float2 *>(W + r0 * F + 8 * j + 2 * t) = make_float2(acc[j][0], acc[j][1]);
-      if (r1 < rows) *reinterpret_cast<float2 *>(W + r1 * F + 8 * j + 2 * t) = make_float2(acc[j][2], acc[j][3]);
-    }
-    __syncwarp();  // everyone is done with this buffer before the next iteration refills it
-    buf ^= 1;
-  }
-  cp_async_wait<0>();
-}
-
 template <int NB>
 int run_whiten_rows(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) {
-  // Default: fp32 FMA (round-to-nearest accumulation).  The mma.sync version below is ~40 us faster per half on C2
-  // but the tensor core truncates its accumulator on every add: measured 3x the error on short rows (7e-6 vs 2e-6
-  // against an fp64 solve), so it stays behind ALS_B200_WHITEN_MMA.
-  if (!getenv("ALS_B200_WHITEN_MMA")) {
-    using C = WhitenCfg<NB>;
-    const int smem = C::SMEM_FLOATS * (int)sizeof(float);
-    auto kern = whiten_rows_kernel<NB>;
+  // fp32 FMA tiles (round-to-nearest accumulation): W = Y Ps into ctx->whitened, Z = Y Ginv into ctx->zfactors
+  using C = WhitenCfg<NB>;
+  const int smem = C::SMEM_FLOATS * (int)sizeof(float);
+  const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), C::RT), (int64_t)ctx->sm_count * 4);
+  {
+    auto kern = whiten_rows_kernel<NB, true>;
     ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), C::RT), (int64_t)ctx->sm_count * 4);
     kern<<<grid, 256, smem, stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
-  } else {
-    using C = WhitenMmaCfg<NB>;
-    const int smem = C::SMEM_FLOATS * (int)sizeof(float);
-    auto kern = whiten_rows_mma_kernel<NB>;
-    ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = (int)std::min<int64_t>(ceil_div(std::max<int64_t>(Y->rows, 1), 16 * kWhitenWarps),
-                                            (int64_t)ctx->sm_count * 2);
-    kern<<<grid, 32 * kWhitenWarps, smem, stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
+    ALS_CUDA(cudaGetLastError());
+    ctx->launches++;
   }
-  ALS_CUDA(cudaGetLastError());
-  ctx->launches++;
+  {
+    auto kern = whiten_rows_kernel<NB, false>;
+    ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 256, smem, stream>>>(Y->d, ctx->Ginv, ctx->zfactors, Y->rows);
+    ALS_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
   return ALS_OK;
 }
 
-// ---- the short-row solver -----------------------------------------------------------------------
+// ---- the batched short-row solver ----------------------------------------------------------------
+constexpr int kBatchWarps = 4;
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Two adjacent values -> packed fp16 (hi) and the packed fp16 remainder (lo): hi + lo carries 22 bits of every
+// value that is not tiny against the fp16 range (see kWScale); both halves are rounded to nearest, so the split is
+// unbiased like the 3xTF32 one of cholesky_device.cuh.
+__device__ __forceinline__ void split_f16x2(float2 x, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(x.x, x.y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// lanes per system for a system of NS unknowns: the register footprint of the distributed upper triangle is
+// G Q (Q + 1) / 2 with Q = NS / G columns per lane -> 72 / 80 / 96 registers
+template <int NS> struct BatchShape;
+template <> struct BatchShape<16> { static constexpr int G = 2; };
+template <> struct BatchShape<32> { static constexpr int G = 8; };
+template <> struct BatchShape<48> { static constexpr int G = 16; };
+
 template <int NB, int NBs>
-struct ShortCfg {
-  using S = Cfg<NBs>;                      // the n x n system, padded to NS
+struct BatchCfg {
+  using S = Cfg<NBs>;                        // tile indexing of the NS x NS Gram matrix
   static constexpr int F = 16 * NB;
   static constexpr int NS = 16 * NBs;
-  static constexpr int NL = (NS + 31) / 32;  // nonzeros held per lane
+  static constexpr int G = BatchShape<NS>::G;
+  static constexpr int B = 32 / G;           // systems per batch
+  static constexpr int Q = NS / G;           // columns per lane
+  static constexpr int TOT = G * Q * (Q + 1) / 2;
   static constexpr int NG = NS / 8;          // 8-row groups of W_u
   static constexpr int KP = 16;              // factor dimensions staged per phase
   static constexpr int NPH = F / KP;
-  static constexpr int LDW = KP + 4;         // conflict-free fragment reads, 16-byte aligned rows
+  static constexpr int LDW = KP + 8;         // conflict-free 8-byte fragment reads, 16-byte aligned rows
   static constexpr int STAGE = NS * LDW;
-  static constexpr int WORK = 2 * STAGE > S::U_FLOATS ? 2 * STAGE : S::U_FLOATS;  // stages, then U, then r
-  static constexpr int WARP_FLOATS = WORK + NS;
-  static constexpr int LDP = F + 4;
-  static constexpr int SMEM_FLOATS = F * LDP + kShortWarps * WARP_FLOATS;
-  static_assert(WORK >= F, "r does not fit");
+  static constexpr int TRI = NS * (NS + 1) / 2;
+  // the B systems of a batch start G banks apart: phase B reads them conflict free
+  static constexpr int SYS = TRI + (((G - TRI % 32) % 32) + 32) % 32;
+  // packed upper triangle, row major: element (i, c), c >= i, lives at roff(i) + c
+  __host__ __device__ static constexpr int roff(int i) { return i * NS - i * (i + 1) / 2; }
+  __host__ __device__ static constexpr int off(int q) { return G * q * (q + 1) / 2; }  // registers of column block q
+  static constexpr int META = B * NS;
+  static constexpr int WARP_FLOATS = 2 * STAGE + B * SYS + 3 * META + 32;
+  static constexpr int SMEM_FLOATS = kBatchWarps * WARP_FLOATS;
+  static_assert((B * NS) % 32 == 0, "prologue loop must be warp uniform");
+  static_assert(2 * STAGE >= F, "x staging");
 };
 
-// phase ph of the gather: 16 factor dimensions of every live 8-row group of W_u -> stage ph & 1
+// Phase B: the B systems of the batch, G lanes each.  Lane l of a group owns the columns c = l + G q of
+// U' = D U (the upper triangle after elimination), rows 0 .. c, in a[off(q) + i]; entries below the diagonal inside
+// the last row block of a column block are storage only (never read as data).  Plain Gaussian elimination on the
+// symmetric matrix (LDL^T: no square roots on the critical path), right-hand side carried along, then a
+// row-oriented back substitution with a G-lane reduction per unknown.
+// compile-time loop: every register index below must be a constant (the loop nests are too large for
+// "#pragma unroll" to be honoured, and a dynamically indexed array would live in local memory)
+template <int I, int N, class Fn>
+__device__ __forceinline__ void static_for(Fn &&f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
 template <class C>
-__device__ __forceinline__ void short_issue(float *wsm, const float *const (&src)[C::NG], int ph, int n, int g, int t) {
-  float *st = wsm + (ph & 1) * C::STAGE;
+__device__ __forceinline__ void batch_solve(const float *__restrict__ sy, float (&z)[C::Q], int l, float (&s)[C::Q]) {
+  constexpr int NS = C::NS, G = C::G, Q = C::Q;
+  constexpr unsigned kFull = 0xffffffffu;
+  float a[C::TOT];
+  float rinvs[Q];
+  static_for<0, Q>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
+    const int c = l + G * q;
+    static_for<0, G *(q + 1)>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      a[C::off(q) + i] = (i <= c) ? sy[C::roff(i) + c] : 0.f;
+    });
+    rinvs[q] = 0.f;
+    s[q] = 0.f;
+  });
+  static_for<0, NS>([&](auto rcn) {
+    constexpr int r = decltype(rcn)::value;
+    constexpr int qr = r / G, lr = r % G;
+    const float d = a[C::off(qr) + r];  // the pivot on lane lr
+    float rc = rcp_approx(d);
+    rc = rc * fmaf(-d, rc, 2.f);
+    const float rinv = __shfl_sync(kFull, rc, lr, G);
+    rinvs[qr] = (l == lr) ? rinv : rinvs[qr];
+    const float zr = __shfl_sync(kFull, z[qr], lr, G);
+    // multipliers of this lane's columns: u[q] = A[r][c] / d_r
+    float u[Q];
+    static_for<qr, Q>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      u[q] = a[C::off(q) + r] * rinv;
+      const float nz = fmaf(-u[q], zr, z[q]);
+      z[q] = (q > qr || l > lr) ? nz : z[q];  // rows after the pivot only
+    });
+    static_for<r + 1, NS>([&](auto r2c) {
+      constexpr int r2 = decltype(r2c)::value;
+      constexpr int q2 = r2 / G, l2 = r2 % G;
+      const float m = __shfl_sync(kFull, u[q2], l2, G);
+      static_for<q2, Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        a[C::off(q) + r2] = fmaf(-m, a[C::off(q) + r], a[C::off(q) + r2]);
+      });
+    });
+  });
+  static_for<0, NS>([&](auto rcn) {
+    constexpr int r = NS - 1 - decltype(rcn)::value;
+    constexpr int qr = r / G, lr = r % G;
+    float part = 0.f;
+    static_for<qr, Q>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      const float term = a[C::off(q) + r] * s[q];
+      part += (q > qr || l > lr) ? term : 0.f;  // columns after r only
+    });
 #pragma unroll
-  for (int q = 0; q < C::NG; ++q)
-    if (8 * q < n) cp_async16(st + (8 * q + g) * C::LDW + 4 * t, src[q] + C::KP * ph);
-  cp_async_commit();
+    for (int o = G / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o, G);
+    const float sr = (z[qr] - part) * rinvs[qr];
+    s[qr] = (l == lr) ? sr : s[qr];
+  });
 }
 
 template <int NB, int NBs>
-__global__ void __launch_bounds__(32 * kShortWarps, NBs == 3 ? 2 : NBs == 2 ? 3 : 4)
-short_rows_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ W,
-                  const float *__restrict__ P, float *__restrict__ X, int64_t row_offset,
-                  const WorkItem *__restrict__ work, int n_work, int32_t *counter, WorkItem *deferred,
-                  int32_t *n_deferred, const int32_t *whiten_ok, float *const *peers, int n_peers) {
-  using C = ShortCfg<NB, NBs>;
+__global__ void __launch_bounds__(32 * kBatchWarps, 3)
+short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ W,
+                   const float *__restrict__ Z, float *__restrict__ X, int64_t row_offset,
+                   const WorkItem *__restrict__ work, int n_work, int32_t *counter, WorkItem *deferred,
+                   int32_t *n_deferred, const int32_t *whiten_ok, float *const *peers, int n_peers) {
+  using C = BatchCfg<NB, NBs>;
   using S = typename C::S;
-  constexpr int F = C::F, NS = C::NS, NL = C::NL, NG = C::NG, LDW = C::LDW, LDP = C::LDP;
+  constexpr int F = C::F, NS = C::NS, G = C::G, B = C::B, Q = C::Q, NG = C::NG, LDW = C::LDW, NPH = C::NPH;
+  constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char short_smem[];
-  float *smem = reinterpret_cast<float *>(short_smem);
-  float *Ps = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  float *wsm = smem + F * LDP + warp * C::WARP_FLOATS;
-  float *zb = wsm + C::WORK;
-  for (int e = threadIdx.x; e < F * F; e += blockDim.x) Ps[(e / F) * LDP + e % F] = __ldg(P + e);
-  __syncthreads();
+  float *wsm = reinterpret_cast<float *>(short_smem) + warp * C::WARP_FLOATS;
+  float *stage = wsm;                                    // 2 stages of W_u; later the x staging is not needed
+  float *sys = stage + 2 * C::STAGE;                     // B packed upper triangles
+  int *idxs = reinterpret_cast<int *>(sys + B * C::SYS);  // [B][NS] column indices (padding repeats a real one)
+  float *es = reinterpret_cast<float *>(idxs + C::META); // [B][NS] sqrt(|c| - 1) / 2^14, 0 on padding
+  float *zs = es + C::META;                              // [B][NS] E^-1 c+, then t = E s
+  unsigned *badbits = reinterpret_cast<unsigned *>(zs + C::META);
   const bool usable = *whiten_ok != 0;
+  const int l = lane % G, sb = lane / G;
 
   for (;;) {
-    int v = 0;
-    if (lane == 0) v = atomicAdd(counter, 1);
-    v = __shfl_sync(0xffffffffu, v, 0);
-    if (v >= n_work) break;
-    const int4 raw = __ldg(reinterpret_cast<const int4 *>(work) + v);
-    const WorkItem wi{raw.x, raw.y, raw.z, raw.w};
-    const int n = wi.k1 - wi.k0;
-    const int64_t xoff = (row_offset + wi.row) * F;
-    auto defer = [&]() {
-      if (lane == 0) deferred[atomicAdd(n_deferred, 1)] = wi;
-    };
-    if (wi.slot != -1 || !usable || n > NS) {
-      defer();
-      continue;
+    int v0 = 0;
+    if (lane == 0) v0 = atomicAdd(counter, B);
+    v0 = __shfl_sync(kFull, v0, 0);
+    if (v0 >= n_work) break;
+    const int nb = min(B, n_work - v0);
+    // lane b keeps item b of the batch
+    WorkItem mine{0, 0, 0, -3};
+    if (lane < nb) {
+      const int4 raw = __ldg(reinterpret_cast<const int4 *>(work) + v0 + lane);
+      mine = WorkItem{raw.x, raw.y, raw.z, raw.w};
     }
-    if (n == 0) {  // no observations: the reference zeroes the row (_als.pyx:98-100)
-      for (int m = lane; m < F; m += 32) {
-        X[xoff + m] = 0.f;
-        for (int pi = 0; pi < n_peers; ++pi) peers[pi][xoff + m] = 0.f;
+    const int my_n = mine.k1 - mine.k0;
+    bool my_defer = lane < nb && (mine.slot != -1 || !usable || my_n > NS);
+    const int my_len = (lane < nb && !my_defer) ? my_n : 0;  // nonzeros this path will use
+    __syncwarp();  // the previous batch is done with the metadata
+    if (lane == 0) *badbits = 0u;
+    __syncwarp();
+    // ---- prologue: the nonzeros of the whole batch -> shared memory (_als.pyx:109-124 semantics)
+#pragma unroll
+    for (int e = lane; e < C::META; e += 32) {
+      const int b = e / NS, i = e % NS;
+      const int k0 = __shfl_sync(kFull, mine.k0, b);
+      const int len = __shfl_sync(kFull, my_len, b);
+      const bool valid = i < len;
+      int id = 0;
+      float c = 1.f;
+      if (valid) {
+        id = __ldg(indices + k0 + i);
+        c = __ldg(data + k0 + i);
+      } else if (len > 0) {
+        id = __ldg(indices + k0);  // padding repeats a real row of W; its weight is 0
       }
-      continue;
-    }
-    // ---- the row's nonzeros: nonzero i lives in slot i / 32 of lane i % 32
-    int idx[NL];
-    float ew[NL], rhs[NL];
-    bool bad = false;
-#pragma unroll
-    for (int sl = 0; sl < NL; ++sl) {
-      const int k = wi.k0 + 32 * sl + lane;
-      const bool valid = k < wi.k1;
-      idx[sl] = valid ? __ldg(indices + k) : -1;
-      const float c = valid ? __ldg(data + k) : 1.f;
       const float w = fabsf(c) - 1.f;  // _als.pyx:115-118
-      bad = bad || !(w >= 0.f);        // negative weight or NaN: not for this path
-      ew[sl] = valid ? sqrtf(fmaxf(w, 1e-10f)) : 0.f;
-      rhs[sl] = (valid && c > 0.f) ? c / ew[sl] : 0.f;  // E^-1 c+   (_als.pyx:119-121: only c > 0 feeds b)
+      if (valid && !(w >= 0.f)) atomicOr(badbits, 1u << b);  // negative weight or NaN: not for this path
+      const float ew = valid ? sqrtf(fmaxf(w, 1e-10f)) : 0.f;
+      idxs[e] = id;
+      es[e] = ew * kWScaleInv;
+      zs[e] = (valid && c > 0.f) ? c / ew : 0.f;  // E^-1 c+   (_als.pyx:119-121: only c > 0 feeds b)
     }
-    if (__any_sync(0xffffffffu, bad)) {
-      defer();
-      continue;
+    __syncwarp();
+    const unsigned bad = *badbits;
+    if (bad) {  // such rows go to the full-size kernel; here they become the identity system
+#pragma unroll
+      for (int e = lane; e < C::META; e += 32)
+        if ((bad >> (e / NS)) & 1u) {
+          es[e] = 0.f;
+          zs[e] = 0.f;
+        }
+      if (lane < nb && ((bad >> lane) & 1u)) my_defer = true;
+      __syncwarp();
     }
-    const int first = __shfl_sync(0xffffffffu, idx[0], 0);
-#pragma unroll
-    for (int sl = 0; sl < NL; ++sl)
-      if (idx[sl] < 0) idx[sl] = first;  // padding repeats a real row; its weight is 0
-    // gather pointers: group q covers W_u rows 8q .. 8q+7, this lane copies chunk (lane & 3) of row 8q + (lane >> 2)
-    const float *src[NG];
-#pragma unroll
-    for (int q = 0; q < NG; ++q) {
-      const int ri = __shfl_sync(0xffffffffu, idx[(8 * q) >> 5], (8 * q + g) & 31);
-      src[q] = W + (int64_t)ri * F + 4 * t;
-    }
-    RowState<NBs> st;
-#pragma unroll
-    for (int e = 0; e < S::NTILES; ++e) st.acc[e][0] = st.acc[e][1] = st.acc[e][2] = st.acc[e][3] = 0.f;
 
-    // ---- K = W_u W_u^T, 16 factor dimensions per phase, double buffered
-    short_issue<C>(wsm, src, 0, n, g, t);
-#pragma unroll  // (cicc 12.9 crashes on this loop when it is kept rolled)
-    for (int ph = 0; ph < C::NPH; ++ph) {
-      if (ph + 1 < C::NPH) {
-        short_issue<C>(wsm, src, ph + 1, n, g, t);
+    // ---- phase A: K = W_u W_u^T for every row of the batch, 16 factor dimensions per phase; the gathers of
+    //      phase p + 1 (possibly the next row's first) are in flight while phase p is multiplied
+    auto issue = [&](int p) {
+      const int b = p / NPH, ph = p % NPH;
+      float *st = stage + (p & 1) * C::STAGE;
+      const int *ix = idxs + b * NS;
+#pragma unroll
+      for (int q = 0; q < NG; ++q) {
+        const int ri = ix[8 * q + g];
+        cp_async16(st + (8 * q + g) * LDW + 4 * t, W + (int64_t)ri * F + C::KP * ph + 4 * t);
+      }
+      cp_async_commit();
+    };
+    float acc[S::NTILES][4];
+#pragma unroll
+    for (int e = 0; e < S::NTILES; ++e) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
+    const int TP = nb * NPH;
+    issue(0);
+    for (int p = 0; p < TP; ++p) {
+      if (p + 1 < TP) {
+        issue(p + 1);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
       }
       __syncwarp();
-      const float *sg = wsm + (ph & 1) * C::STAGE;
-#pragma unroll
-      for (int kk = 0; kk < C::KP; kk += 8) {
-        uint32_t vh0[S::NT8], vl0[S::NT8], vh1[S::NT8], vl1[S::NT8];
+      const float *sg = stage + (p & 1) * C::STAGE;
+      {
+        uint32_t h0[S::NT8], h1[S::NT8], l0[S::NT8], l1[S::NT8];
 #pragma unroll
         for (int c = 0; c < S::NT8; ++c) {
-          split_tf32(sg[(8 * c + g) * LDW + kk + t], vh0[c], vl0[c]);
-          split_tf32(sg[(8 * c + g) * LDW + kk + t + 4], vh1[c], vl1[c]);
+          split_f16x2(*reinterpret_cast<const float2 *>(sg + (8 * c + g) * LDW + 2 * t), h0[c], l0[c]);
+          split_f16x2(*reinterpret_cast<const float2 *>(sg + (8 * c + g) * LDW + 2 * t + 8), h1[c], l1[c]);
         }
 #pragma unroll
-        for (int term = 0; term < 3; ++term) {
+        for (int term = 0; term < 3; ++term) {  // lo * hi, hi * lo, hi * hi: the chain through a tile is a sweep apart
 #pragma unroll
           for (int i = 0; i < NBs; ++i) {
-            const uint32_t a0 = term == 0 ? vl0[2 * i] : vh0[2 * i];
-            const uint32_t a1 = term == 0 ? vl0[2 * i + 1] : vh0[2 * i + 1];
-            const uint32_t a2 = term == 0 ? vl1[2 * i] : vh1[2 * i];
-            const uint32_t a3 = term == 0 ? vl1[2 * i + 1] : vh1[2 * i + 1];
+            const uint32_t a0 = term == 0 ? l0[2 * i] : h0[2 * i];
+            const uint32_t a1 = term == 0 ? l0[2 * i + 1] : h0[2 * i + 1];
+            const uint32_t a2 = term == 0 ? l1[2 * i] : h1[2 * i];
+            const uint32_t a3 = term == 0 ? l1[2 * i + 1] : h1[2 * i + 1];
 #pragma unroll
             for (int j = 2 * i; j < S::NT8; ++j) {
-              float(&d)[4] = st.acc[S::tidx(i, j)];
-              if (term == 1) mma_tf32(d, a0, a1, a2, a3, vl0[j], vl1[j]);
-              else mma_tf32(d, a0, a1, a2, a3, vh0[j], vh1[j]);
+              float(&d)[4] = acc[S::tidx(i, j)];
+              if (term == 1) mma_f16(d, a0, a1, a2, a3, l0[j], l1[j]);
+              else mma_f16(d, a0, a1, a2, a3, h0[j], h1[j]);
             }
           }
         }
       }
-      __syncwarp();  // the stage is free for phase ph + 2
-    }
-
-    // ---- M = I + E K E on the n x n leading block, identity on the padding; rhs = E^-1 c+
+      if (p % NPH == NPH - 1) {
+        // ---- M = I + E K E (identity on the padding: e = 0 there) -> the packed upper triangle of system b
+        const int b = p / NPH;
+        float *sy = sys + b * C::SYS;
+        const float *eb = es + b * NS;
 #pragma unroll
-    for (int i = 0; i < NBs; ++i) {
-      const int r0 = 16 * i + g, r1 = r0 + 8;
-      const float er0 = __shfl_sync(0xffffffffu, ew[(16 * i) >> 5], r0 & 31);
-      const float er1 = __shfl_sync(0xffffffffu, ew[(16 * i) >> 5], r1 & 31);
+        for (int i = 0; i < NBs; ++i) {
+          const int r0 = 16 * i + g, r1 = r0 + 8;
+          const float er0 = eb[r0], er1 = eb[r1];
+          const int ro0 = r0 * NS - ((r0 * (r0 + 1)) >> 1), ro1 = r1 * NS - ((r1 * (r1 + 1)) >> 1);
 #pragma unroll
-      for (int j = 2 * i; j < S::NT8; ++j) {
-        const int c0 = 8 * j + 2 * t, c1 = c0 + 1;
-        const float ec0 = __shfl_sync(0xffffffffu, ew[(8 * j) >> 5], c0 & 31);
-        const float ec1 = __shfl_sync(0xffffffffu, ew[(8 * j) >> 5], c1 & 31);
-        float(&d)[4] = st.acc[S::tidx(i, j)];
-        d[0] = (r0 < n && c0 < n ? er0 * ec0 * d[0] : 0.f) + (r0 == c0 ? 1.f : 0.f);
-        d[1] = (r0 < n && c1 < n ? er0 * ec1 * d[1] : 0.f) + (r0 == c1 ? 1.f : 0.f);
-        d[2] = (r1 < n && c0 < n ? er1 * ec0 * d[2] : 0.f) + (r1 == c0 ? 1.f : 0.f);
-        d[3] = (r1 < n && c1 < n ? er1 * ec1 * d[3] : 0.f) + (r1 == c1 ? 1.f : 0.f);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < S::NT8; ++c) {
-      const float bv = __shfl_sync(0xffffffffu, rhs[(8 * c) >> 5], (8 * c + g) & 31);
-      st.bp[c] = t == 0 ? bv : 0.f;  // factor_solve sums bp over the 4 lanes of a group
-    }
-
-    // ---- M s = rhs
-    bool ok = true;
-    float s[NL];
-    factor_solve<NBs>(st, wsm, zb, lane, ok, 0, s);
-    if (!ok) {  // cannot happen for finite inputs (M >= I); let the full-size path decide
-      defer();
-      __syncwarp();
-      continue;
-    }
-
-    // ---- r = W_u^T (E s): lane owns columns 2 lane, 2 lane + 1
-    float r0 = 0.f, r1 = 0.f;
-    const bool owns = 2 * lane < F;
-#pragma unroll
-    for (int sl = 0; sl < NL; ++sl) {
-      const float tc = ew[sl] * s[sl];
-      const int cnt = min(32, n - 32 * sl);
-#pragma unroll 8
-      for (int i = 0; i < cnt; ++i) {
-        const float ti = __shfl_sync(0xffffffffu, tc, i);
-        const int ri = __shfl_sync(0xffffffffu, idx[sl], i);
-        if (owns) {
-          const float2 w2 = __ldcg(reinterpret_cast<const float2 *>(W + (int64_t)ri * F) + lane);
-          r0 = fmaf(ti, w2.x, r0);
-          r1 = fmaf(ti, w2.y, r1);
+          for (int j = 2 * i; j < S::NT8; ++j) {
+            const int c0 = 8 * j + 2 * t, c1 = c0 + 1;
+            const float2 ec = *reinterpret_cast<const float2 *>(eb + c0);
+            float(&d)[4] = acc[S::tidx(i, j)];
+            if (c0 >= r0) sy[ro0 + c0] = fmaf(er0 * ec.x, d[0], r0 == c0 ? 1.f : 0.f);
+            if (c1 >= r0) sy[ro0 + c1] = fmaf(er0 * ec.y, d[1], r0 == c1 ? 1.f : 0.f);
+            if (c0 >= r1) sy[ro1 + c0] = fmaf(er1 * ec.x, d[2], r1 == c0 ? 1.f : 0.f);
+            if (c1 >= r1) sy[ro1 + c1] = fmaf(er1 * ec.y, d[3], r1 == c1 ? 1.f : 0.f);
+            d[0] = d[1] = d[2] = d[3] = 0.f;
+          }
         }
       }
+      __syncwarp();  // the stage is free for phase p + 2
     }
-    __syncwarp();
-    if (owns) *reinterpret_cast<float2 *>(wsm + 2 * lane) = make_float2(r0, r1);
-    __syncwarp();
-    // ---- x = P r, P upper triangular: row m = lane + 32 q needs columns k >= m (>= 32 q for the whole slot)
-    constexpr int QF = (F + 31) / 32;
-    float xx[QF];
+
+    // ---- phase B: all systems of the batch at once, G lanes per system
+    bool fin = true;
+    {
+      float z[Q], e[Q], s[Q];
 #pragma unroll
-    for (int q = 0; q < QF; ++q) {
-      const int m = lane + 32 * q;
-      const float *prow = Ps + (m < F ? m : 0) * LDP;
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int k = 32 * q; k < F; k += 8) {
-        const float4 p0 = *reinterpret_cast<const float4 *>(prow + k);
-        const float4 p1 = *reinterpret_cast<const float4 *>(prow + k + 4);
-        const float4 q0 = *reinterpret_cast<const float4 *>(wsm + k);
-        const float4 q1 = *reinterpret_cast<const float4 *>(wsm + k + 4);
-        a0 = fmaf(p0.x, q0.x, fmaf(p0.y, q0.y, fmaf(p0.z, q0.z, fmaf(p0.w, q0.w, a0))));
-        a1 = fmaf(p1.x, q1.x, fmaf(p1.y, q1.y, fmaf(p1.z, q1.z, fmaf(p1.w, q1.w, a1))));
+      for (int q = 0; q < Q; ++q) {
+        z[q] = zs[sb * NS + l + G * q];
+        e[q] = es[sb * NS + l + G * q];
       }
-      xx[q] = a0 + a1;
+      batch_solve<C>(sys + sb * C::SYS, z, l, s);
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const float tq = e[q] * s[q] * kWScale;  // t = E s
+        fin = fin && (fabsf(tq) <= 3.0e38f);      // false for inf and NaN
+        zs[sb * NS + l + G * q] = tq;
+      }
     }
-    store_solution<F>(xx, X + xoff, lane, peers, n_peers, xoff);
-    __syncwarp();  // r is dead; the next row may overwrite the work area
+    const unsigned notfin = __ballot_sync(kFull, !fin);
+    if (lane < nb && ((notfin >> (lane * G)) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u))))
+      my_defer = true;  // cannot happen for finite inputs (M >= I); let the full-size path decide
+    if (lane < nb && my_defer) deferred[atomicAdd(n_deferred, 1)] = mine;
+    __syncwarp();
+
+    // ---- phase C: x = Z_u^T t, lane owns columns 2 lane, 2 lane + 1
+    const bool owns = 2 * lane < F;
+    for (int b = 0; b < nb; ++b) {
+      if (__shfl_sync(kFull, (int)my_defer, b)) continue;
+      const int row = __shfl_sync(kFull, mine.row, b);
+      const int n = __shfl_sync(kFull, my_n, b);
+      const int64_t xoff = (row_offset + row) * F;
+      float x0 = 0.f, x1 = 0.f;  // no observations: the reference zeroes the row (_als.pyx:98-100)
+      const int *ix = idxs + b * NS;
+      const float *tv = zs + b * NS;
+      for (int i0 = 0; i0 < n; i0 += 8) {  // the padding up to a multiple of 8 has t = 0 and a valid index
+        const int4 ia = *reinterpret_cast<const int4 *>(ix + i0), ib = *reinterpret_cast<const int4 *>(ix + i0 + 4);
+        const float4 ta = *reinterpret_cast<const float4 *>(tv + i0), tb = *reinterpret_cast<const float4 *>(tv + i0 + 4);
+        const int id[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+        const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+        float2 zz[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          zz[u] = owns ? __ldcg(reinterpret_cast<const float2 *>(Z + (int64_t)id[u] * F) + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          x0 = fmaf(tt[u], zz[u].x, x0);
+          x1 = fmaf(tt[u], zz[u].y, x1);
+        }
+      }
+      if (owns) {
+        *reinterpret_cast<float2 *>(X + xoff + 2 * lane) = make_float2(x0, x1);
+        for (int pi = 0; pi < n_peers; ++pi) *reinterpret_cast<float2 *>(peers[pi] + xoff + 2 * lane) = make_float2(x0, x1);
+      }
+    }
   }
 }
 
 template <int NB, int NBs>
 int run_short(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, int64_t count, int slot, cudaStream_t stream) {
-  using C = ShortCfg<NB, NBs>;
+  using C = BatchCfg<NB, NBs>;
   if (count <= 0) return ALS_OK;
   const int smem = C::SMEM_FLOATS * (int)sizeof(float);
-  auto kern = short_rows_kernel<NB, NBs>;
+  auto kern = short_batch_kernel<NB, NBs>;
   ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int ctas_per_sm = 0;
-  ALS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * kShortWarps, smem));
+  ALS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * kBatchWarps, smem));
   if (ctas_per_sm < 1) {
     set_error("short rows: kernel does not fit on an SM (smem %d bytes)", smem);
     return ALS_E_CUDA;
   }
-  const int grid = (int)std::min<int64_t>(ceil_div(count, kShortWarps), (int64_t)ctx->sm_count * ctas_per_sm);
-  kern<<<grid, 32 * kShortWarps, smem, stream>>>(Cm->indices, Cm->data, ctx->whitened, ctx->Pinv, X->d, Cm->row_offset,
-                                                       Cm->work + begin, (int)count, ctx->counters + kCtrShort + slot,
-                                                       ctx->deferred, ctx->counters + kCtrDeferredCount,
-                                                       ctx->counters + kCtrWhitenOk, X->peers_dev, X->n_peers);
+  const int grid = (int)std::min<int64_t>(ceil_div(count, (int64_t)kBatchWarps * C::B), (int64_t)ctx->sm_count * ctas_per_sm);
+  kern<<<grid, 32 * kBatchWarps, smem, stream>>>(Cm->indices, Cm->data, ctx->whitened, ctx->zfactors, X->d, Cm->row_offset,
+                                                  Cm->work + begin, (int)count, ctx->counters + kCtrShort + slot,
+                                                  ctx->deferred, ctx->counters + kCtrDeferredCount,
+                                                  ctx->counters + kCtrWhitenOk, X->peers_dev, X->n_peers);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
   return ALS_OK;
@@ -533,11 +584,16 @@ int short_rows_prepare(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) 
   int rc = ensure_device_buffer(ctx, (void **)&ctx->whitened, &ctx->whitened_bytes,
                                 std::max<int64_t>(Y->rows, 1) * F * (int64_t)sizeof(float));
   if (rc != ALS_OK) return rc;
-  const int smem = F * (2 * F + 1) * (int)sizeof(double);
+  rc = ensure_device_buffer(ctx, (void **)&ctx->zfactors, &ctx->zfactors_bytes,
+                            std::max<int64_t>(Y->rows, 1) * F * (int64_t)sizeof(float));
+  if (rc != ALS_OK) return rc;
+  const int smem = (F * (2 * F + 1) + F * (F + 1)) * (int)sizeof(double);
   ALS_CUDA(cudaFuncSetAttribute(whiten_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  whiten_factor_kernel<<<1, 1024, smem, stream>>>(ctx->Greg, F, ctx->Pinv, ctx->counters + kCtrWhitenOk);
+  whiten_factor_kernel<<<1, 1024, smem, stream>>>(ctx->Greg, F, ctx->Pinv, ctx->Ginv, ctx->counters + kCtrWhitenOk);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
+  // 64 padded factors: one pass on the tcgen05 tensor cores (dense.cu); the whiten_fma knob keeps the fp32 FMA tiles
+  if (F == 64 && !ctx->knobs.whiten_fma) return launch_dense_whiten(ctx, Y, stream);
   switch (F / 16) {
     case 2: return run_whiten_rows<2>(ctx, Y, stream);
     case 3: return run_whiten_rows<3>(ctx, Y, stream);

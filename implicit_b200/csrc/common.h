@@ -50,8 +50,19 @@ constexpr int kChunkNnz = 2048;   // ... into chunks of this many nonzeros (mult
 
 }  // namespace als
 
+// Measurement knobs.  Read from the environment ONCE, in als_ctx_create (which reports every knob that is set on
+// stderr); tools flip them afterwards with als_ctx_set_knob.  None changes results beyond fp32 rounding.
+struct als_knobs {
+  int short_max = 48;         // ALS_B200_SHORT_MAX: longest row (nonzeros) of the n x n short-row path: 0 / 16 / 32 / 48
+  int short_serial = 0;       // ALS_B200_SHORT_SERIAL: short-row kernels on the compute stream instead of the aux stream
+  int whiten_fma = 0;         // ALS_B200_WHITEN_FMA: fp32 FMA tiles for W = Y P, Z = Y G^-1 instead of the tcgen05 apply
+  int gramian_mma = 0;        // ALS_B200_GRAMIAN_MMA: legacy mma.sync Gramian
+  int cg_nv = 2;              // ALS_B200_CG_NV: float4 words per lane of the CG kernel (1 / 2 / 4)
+};
+
 struct als_ctx {
   int device = 0;
+  als_knobs knobs;
   int sm_count = 0;
   int64_t l2_bytes = 0;
   int64_t mem_bytes = 0;
@@ -73,9 +84,13 @@ struct als_ctx {
   double *dscalars = nullptr;  // loss accumulators (8 doubles)
   // short-row path of the Cholesky half (cholesky_short.cu): P = R^-1 with G + lambda I = R^T R, the whitened
   // factors W = Y P, and the list of short items handed back to the full-size kernel
-  float *Pinv = nullptr;
-  float *whitened = nullptr;
+  float *Pinv = nullptr;      // 2^14 P (upper triangular)
+  float *Ginv = nullptr;      // G^-1 = P P^T
+  float *whitened = nullptr;  // W = Y (2^14 P)
   int64_t whitened_bytes = 0;
+  float *zfactors = nullptr;  // Z = Y G^-1
+  int64_t zfactors_bytes = 0;
+  float *dense_bt = nullptr;  // [2^14 P | G^-1]^T split into TF32 hi / lo parts for the tcgen05 apply (dense.cu)
   als::WorkItem *deferred = nullptr;
   int64_t deferred_cap = 0;
   // generic scratch (giant-row partial slots, L2 flush, top-k staging)
@@ -171,6 +186,8 @@ int launch_cholesky_wide(als_ctx *ctx, const als_csr *C, als_factors *X, const a
 // short-row path (cholesky_short.cu).  prepare: P and W from ctx->Greg and Y.  launch: items [begin, n_work) of
 // C->work, all of at most `max_len` nonzeros; whatever it cannot take lands in ctx->deferred / counters[kCtrDeferredCount].
 int short_rows_prepare(als_ctx *ctx, const als_factors *Y, cudaStream_t stream);
+// W = Y (2^14 P) and Z = Y G^-1 in one pass on the tcgen05 tensor cores (dense.cu; 64 padded factors)
+int launch_dense_whiten(als_ctx *ctx, const als_factors *Y, cudaStream_t stream);
 int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len,
                       cudaStream_t stream);
 int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps);

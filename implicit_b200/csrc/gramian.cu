@@ -246,7 +246,7 @@ int launch_gramian(als_ctx *ctx, const als_factors *Y) {
   }
   // The mma.sync version is ~25 % faster but the tensor core truncates its fp32 accumulator on every add, which
   // biases the all-positive diagonal of G by ~1e-6 relative; the FMA version (round to nearest) is the default.
-  const bool mma = F <= 64 && getenv("ALS_B200_GRAMIAN_MMA") != nullptr;
+  const bool mma = F <= 64 && ctx->knobs.gramian_mma;
   const int64_t steps = mma ? ceil_div(std::max<int64_t>(Y->rows, 1), 8 * kGramWarps)
                             : ceil_div(std::max<int64_t>(Y->rows, 1), kGramRows);
   const int grid = (int)std::min<int64_t>(steps, (int64_t)ctx->sm_count * (mma ? 1 : 2));

@@ -56,6 +56,13 @@ int als_device_count(void);
 /* Replaces implicit/gpu/__init__.py HAS_CUDA probe + per-object device selection (matrix.cu:241). */
 int als_ctx_create(int device, als_ctx **out);
 int als_ctx_destroy(als_ctx *ctx);
+
+/* Measurement knobs ("short_max" 0/16/32/48, "short_serial", "whiten_fma", "gramian_mma", "cg_nv" 1/2/4).  The
+ * environment variables ALS_B200_<KNOB> are read once, in als_ctx_create, and reported on stderr when set; this
+ * call changes a knob afterwards (A/B tools).  Results do not depend on any knob beyond fp32 rounding.
+ * (No reference equivalent.) */
+int als_ctx_set_knob(als_ctx *ctx, const char *name, int value);
+
 /* Join the ctx streams (replaces the cudaDeviceSynchronize after every call, implicit/gpu/als.cu:147,151,196). */
 int als_sync(als_ctx *ctx);
 /* name[256]; sm count; L2 bytes; total global memory bytes. */
@@ -126,6 +133,12 @@ int als_least_squares(als_ctx *ctx, const als_csr *C, als_factors *X, const als_
  * implicit/cpu/_als.pyx:76 (recalculate_user / partial_fit, implicit/cpu/als.py:221-240). */
 int als_least_squares_with_gramian(als_ctx *ctx, const float *YtY_host, const als_csr *C, als_factors *X,
                                    const als_factors *Y, double regularization, int64_t *bad_row);
+
+/* The per-half preprocessing of the short-row path, downloaded: W = Y P with Y^T Y + reg I = R^T R, P = R^-1
+ * (whitened factors) and Z = Y (Y^T Y + reg I)^-1, both rows x factors floats.  Produced on the tcgen05
+ * tensor cores for 64 padded factors (csrc/dense.cu).  Test / tooling entry: the reference has no
+ * counterpart (it forms every row's F x F normal equations, implicit/cpu/_als.pyx:96-130). */
+int als_whitened_factors(als_ctx *ctx, const als_factors *Y, double regularization, float *W_host, float *Z_host);
 
 /* Multi-GPU variants: the Gramian is accumulated over each rank's OWN rows [row0, row0 + nrows) of Y and
  * summed across ranks (ncclAllReduce of f x f floats on the ctx stream, which also orders this rank after

@@ -11,7 +11,7 @@ C = _lib.DeviceCSR.upload(ctx, Cui); T = C.transpose()
 X, Y = _lib.DeviceFactors.from_host(ctx, X0), _lib.DeviceFactors.from_host(ctx, Y0)
 Cs = C.slice_rows(0, cfg["users"] // parts); Ts = T.slice_rows(0, cfg["items"] // parts)
 for lim in ("0", "48"):
-    os.environ["ALS_B200_SHORT_MAX"] = lim
+    ctx.set_knob("short_max", int(lim))
     ctx.profile(True)
     for it in range(4):
         if it == 1: ctx.profile_read()

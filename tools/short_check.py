@@ -19,10 +19,8 @@ sample = np.arange(0, cfg["users"], 197)
 truth = None
 base = None
 for lim in (sys.argv[1:] or ["0", "32", "48s", "48"]):
-    os.environ["ALS_B200_SHORT_MAX"] = lim.rstrip("s")
-    os.environ.pop("ALS_B200_SHORT_SERIAL", None)
-    if lim.endswith("s"):  # "48s": short-row kernels serialised behind the full-size kernel (no aux stream)
-        os.environ["ALS_B200_SHORT_SERIAL"] = "1"
+    ctx.set_knob("short_max", int(lim.rstrip("s")))
+    ctx.set_knob("short_serial", 1 if lim.endswith("s") else 0)  # "48s": short-row kernels on the compute stream
     ctx.profile(True)
     for it in range(4):  # 3 timed cold-start iterations (same state every time, like bench.py's device arm)
         X.upload(X0); Y.upload(Y0)
