@@ -1,4 +1,5 @@
 // C-ABI entry points, device containers and the launch schedule (host side of libals_b200.so).
+#include <cuda_fp16.h>
 #include <limits.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -126,7 +127,7 @@ int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr) {
     items.swap(sorted);
   }
   csr->n_work = (int64_t)items.size();
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < kNumShortThresholds; ++c) {
     int64_t lo = 0, hi = csr->n_work;  // first item of length <= kShortThresholds[c]
     while (lo < hi) {
       const int64_t mid = (lo + hi) / 2;
@@ -237,7 +238,7 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   {
     struct { const char *env; const char *name; } table[] = {
         {"ALS_B200_SHORT_MAX", "short_max"}, {"ALS_B200_SHORT_SERIAL", "short_serial"}, {"ALS_B200_WHITEN_FMA", "whiten_fma"},
-        {"ALS_B200_GRAMIAN_MMA", "gramian_mma"}, {"ALS_B200_CG_NV", "cg_nv"}};
+        {"ALS_B200_GRAMIAN_MMA", "gramian_mma"}, {"ALS_B200_GRAMIAN_FMA", "gramian_fma"}, {"ALS_B200_CG_NV", "cg_nv"}};
     for (const auto &t : table) {
       const char *e = getenv(t.env);
       if (!e) continue;
@@ -285,6 +286,7 @@ ALS_API int als_ctx_set_knob(als_ctx *ctx, const char *name, int value) {
   else if (!strcmp(name, "short_serial")) k.short_serial = value != 0;
   else if (!strcmp(name, "whiten_fma")) k.whiten_fma = value != 0;
   else if (!strcmp(name, "gramian_mma")) k.gramian_mma = value != 0;
+  else if (!strcmp(name, "gramian_fma")) k.gramian_fma = value != 0;
   else if (!strcmp(name, "cg_nv")) {
     ALS_REQUIRE(value == 1 || value == 2 || value == 4, "als_ctx_set_knob: cg_nv must be 1, 2 or 4");
     k.cg_nv = value;
@@ -807,10 +809,21 @@ ALS_API int als_whitened_factors(als_ctx *ctx, const als_factors *Y, double regu
     ALS_CUDA(cudaMemcpyAsync(tmp.data(), which ? ctx->zfactors : ctx->whitened, sizeof(float) * tmp.size(),
                              cudaMemcpyDeviceToHost, ctx->stream));
     ALS_CUDA(cudaStreamSynchronize(ctx->stream));
-    float *dst = which ? Z_host : W_host;
-    const float scale = which ? 1.f : 1.f / 16384.f;
-    for (int64_t r = 0; r < Y->rows; ++r)
-      for (int j = 0; j < Y->f; ++j) dst[r * Y->f + j] = tmp[(size_t)r * Y->ld + j] * scale;
+    if (which) {
+      for (int64_t r = 0; r < Y->rows; ++r)
+        for (int j = 0; j < Y->f; ++j) Z_host[r * Y->f + j] = tmp[(size_t)r * Y->ld + j];
+    } else {
+      // W is stored split and scaled: per 16 dimensions 8 words of fp16 pairs "hi", then 8 words "lo", of 2^14 W
+      for (int64_t r = 0; r < Y->rows; ++r) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(tmp.data() + (size_t)r * Y->ld);
+        for (int j = 0; j < Y->f; ++j) {
+          const uint32_t hi = row[(j / 16) * 16 + (j % 16) / 2], lo = row[(j / 16) * 16 + 8 + (j % 16) / 2];
+          const int sh = (j & 1) ? 16 : 0;
+          const __half_raw hr{(unsigned short)(hi >> sh)}, lr{(unsigned short)(lo >> sh)};
+          W_host[r * Y->f + j] = (__half2float(__half(hr)) + __half2float(__half(lr))) * (1.f / 16384.f);
+        }
+      }
+    }
   }
   if (!ok) {
     set_error("als_whitened_factors: Y^T Y + reg I is not positive definite");

@@ -167,6 +167,38 @@ __global__ void __launch_bounds__(256) whiten_rows_kernel(const float *__restric
   }
 }
 
+// fp32 W rows (the FMA fallback of run_whiten_rows) -> the split format the batch kernel gathers: per 16 factor
+// dimensions 8 words of fp16 pairs "hi" followed by 8 words "lo" (hi + lo carries 22 bits; both rounded to nearest)
+__device__ __forceinline__ void split_f16x2(float2 x, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(x.x, x.y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+__global__ void __launch_bounds__(256) w_split_kernel(float *__restrict__ W, int64_t n_blocks16) {
+  // one thread per (row, 16-dimension block): reads its 16 floats, writes its 16 words in place
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_blocks16; e += (int64_t)gridDim.x * blockDim.x) {
+    float4 *p = reinterpret_cast<float4 *>(W + e * 16);
+    const float4 a = p[0], b = p[1], c = p[2], d = p[3];
+    uint32_t hi[8], lo[8];
+    split_f16x2(make_float2(a.x, a.y), hi[0], lo[0]);
+    split_f16x2(make_float2(a.z, a.w), hi[1], lo[1]);
+    split_f16x2(make_float2(b.x, b.y), hi[2], lo[2]);
+    split_f16x2(make_float2(b.z, b.w), hi[3], lo[3]);
+    split_f16x2(make_float2(c.x, c.y), hi[4], lo[4]);
+    split_f16x2(make_float2(c.z, c.w), hi[5], lo[5]);
+    split_f16x2(make_float2(d.x, d.y), hi[6], lo[6]);
+    split_f16x2(make_float2(d.z, d.w), hi[7], lo[7]);
+    uint4 *o = reinterpret_cast<uint4 *>(p);
+    o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    o[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    o[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    o[3] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
 template <int NB>
 int run_whiten_rows(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) {
   // fp32 FMA tiles (round-to-nearest accumulation): W = Y Ps into ctx->whitened, Z = Y Ginv into ctx->zfactors
@@ -178,7 +210,10 @@ int run_whiten_rows(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) {
     ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, 256, smem, stream>>>(Y->d, ctx->Pinv, ctx->whitened, Y->rows);
     ALS_CUDA(cudaGetLastError());
-    ctx->launches++;
+    const int64_t n16 = std::max<int64_t>(Y->rows, 1) * (C::F / 16);
+    w_split_kernel<<<(int)std::min<int64_t>(ceil_div(n16, 256), (int64_t)ctx->sm_count * 8), 256, 0, stream>>>(ctx->whitened, n16);
+    ALS_CUDA(cudaGetLastError());
+    ctx->launches += 2;
   }
   {
     auto kern = whiten_rows_kernel<NB, false>;
@@ -201,37 +236,32 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1,
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Two adjacent values -> packed fp16 (hi) and the packed fp16 remainder (lo): hi + lo carries 22 bits of every
-// value that is not tiny against the fp16 range (see kWScale); both halves are rounded to nearest, so the split is
-// unbiased like the 3xTF32 one of cholesky_device.cuh.
-__device__ __forceinline__ void split_f16x2(float2 x, uint32_t &hi, uint32_t &lo) {
-  const __half2 h = __floats2half2_rn(x.x, x.y);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
-  hi = *reinterpret_cast<const uint32_t *>(&h);
-  lo = *reinterpret_cast<const uint32_t *>(&l);
-}
-
 // lanes per system for a system of NS unknowns: the register footprint of the distributed upper triangle is
-// G Q (Q + 1) / 2 with Q = NS / G columns per lane -> 72 / 80 / 96 registers
+// G Q (Q + 1) / 2 with Q = NS / G columns per lane -> 36 / 72 / 84 / 80 / 120 / 96 registers
 template <int NS> struct BatchShape;
+template <> struct BatchShape<8> { static constexpr int G = 1; };
 template <> struct BatchShape<16> { static constexpr int G = 2; };
+template <> struct BatchShape<24> { static constexpr int G = 4; };
 template <> struct BatchShape<32> { static constexpr int G = 8; };
+template <> struct BatchShape<40> { static constexpr int G = 8; };
 template <> struct BatchShape<48> { static constexpr int G = 16; };
 
-template <int NB, int NBs>
+template <int NB, int NS_>
 struct BatchCfg {
-  using S = Cfg<NBs>;                        // tile indexing of the NS x NS Gram matrix
   static constexpr int F = 16 * NB;
-  static constexpr int NS = 16 * NBs;
+  static constexpr int NS = NS_;
   static constexpr int G = BatchShape<NS>::G;
   static constexpr int B = 32 / G;           // systems per batch
   static constexpr int Q = NS / G;           // columns per lane
   static constexpr int TOT = G * Q * (Q + 1) / 2;
-  static constexpr int NG = NS / 8;          // 8-row groups of W_u
+  static constexpr int NT8 = NS / 8;         // 8-row groups of W_u == 8-column tiles of the Gram matrix
+  static constexpr int NM = (NS + 15) / 16;  // 16-row tiles (the last one is half empty when NT8 is odd)
+  // upper-triangular tile list: tile (i, j), j >= 2 i
+  __host__ __device__ static constexpr int tidx(int i, int j) { return i * NT8 - i * (i - 1) + (j - 2 * i); }
+  static constexpr int NTILES = tidx(NM - 1, NT8 - 1) + 1;
   static constexpr int KP = 16;              // factor dimensions staged per phase
   static constexpr int NPH = F / KP;
-  static constexpr int LDW = KP + 8;         // conflict-free 8-byte fragment reads, 16-byte aligned rows
+  static constexpr int LDW = 20;             // words per staged row: 8 hi + 8 lo + 4 (conflict-free fragment reads)
   static constexpr int STAGE = NS * LDW;
   static constexpr int TRI = NS * (NS + 1) / 2;
   // the B systems of a batch start G banks apart: phase B reads them conflict free
@@ -243,7 +273,7 @@ struct BatchCfg {
   static constexpr int WARP_FLOATS = 2 * STAGE + B * SYS + 3 * META + 32;
   static constexpr int SMEM_FLOATS = kBatchWarps * WARP_FLOATS;
   static_assert((B * NS) % 32 == 0, "prologue loop must be warp uniform");
-  static_assert(2 * STAGE >= F, "x staging");
+  static_assert(WARP_FLOATS % 4 == 0 && STAGE % 2 == 0 && (B * SYS) % 4 == 0 && META % 4 == 0, "alignment");
 };
 
 // Phase B: the B systems of the batch, G lanes each.  Lane l of a group owns the columns c = l + G q of
@@ -281,11 +311,10 @@ __device__ __forceinline__ void batch_solve(const float *__restrict__ sy, float 
     constexpr int r = decltype(rcn)::value;
     constexpr int qr = r / G, lr = r % G;
     const float d = a[C::off(qr) + r];  // the pivot on lane lr
-    float rc = rcp_approx(d);
-    rc = rc * fmaf(-d, rc, 2.f);
-    const float rinv = __shfl_sync(kFull, rc, lr, G);
+    const float rc = rcp_approx(d);  // within an ulp or two of 1 / d: as good as the division LAPACK would do here
+    const float rinv = G > 1 ? __shfl_sync(kFull, rc, lr, G) : rc;
     rinvs[qr] = (l == lr) ? rinv : rinvs[qr];
-    const float zr = __shfl_sync(kFull, z[qr], lr, G);
+    const float zr = G > 1 ? __shfl_sync(kFull, z[qr], lr, G) : z[qr];
     // multipliers of this lane's columns: u[q] = A[r][c] / d_r
     float u[Q];
     static_for<qr, Q>([&](auto qc) {
@@ -297,7 +326,7 @@ __device__ __forceinline__ void batch_solve(const float *__restrict__ sy, float 
     static_for<r + 1, NS>([&](auto r2c) {
       constexpr int r2 = decltype(r2c)::value;
       constexpr int q2 = r2 / G, l2 = r2 % G;
-      const float m = __shfl_sync(kFull, u[q2], l2, G);
+      const float m = G > 1 ? __shfl_sync(kFull, u[q2], l2, G) : u[q2];
       static_for<q2, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
         a[C::off(q) + r2] = fmaf(-m, a[C::off(q) + r], a[C::off(q) + r2]);
@@ -320,25 +349,24 @@ __device__ __forceinline__ void batch_solve(const float *__restrict__ sy, float 
   });
 }
 
-template <int NB, int NBs>
+template <int NB, int NS>
 __global__ void __launch_bounds__(32 * kBatchWarps, 3)
-short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ W,
+short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const uint32_t *__restrict__ W,
                    const float *__restrict__ Z, float *__restrict__ X, int64_t row_offset,
                    const WorkItem *__restrict__ work, int n_work, int32_t *counter, WorkItem *deferred,
                    int32_t *n_deferred, const int32_t *whiten_ok, float *const *peers, int n_peers) {
-  using C = BatchCfg<NB, NBs>;
-  using S = typename C::S;
-  constexpr int F = C::F, NS = C::NS, G = C::G, B = C::B, Q = C::Q, NG = C::NG, LDW = C::LDW, NPH = C::NPH;
+  using C = BatchCfg<NB, NS>;
+  constexpr int F = C::F, G = C::G, B = C::B, Q = C::Q, NT8 = C::NT8, NM = C::NM, LDW = C::LDW, NPH = C::NPH;
   constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char short_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   float *wsm = reinterpret_cast<float *>(short_smem) + warp * C::WARP_FLOATS;
-  float *stage = wsm;                                    // 2 stages of W_u; later the x staging is not needed
-  float *sys = stage + 2 * C::STAGE;                     // B packed upper triangles
+  uint32_t *stage = reinterpret_cast<uint32_t *>(wsm);   // 2 stages of W_u: per row 8 fp16-pair words hi, 8 lo
+  float *sys = wsm + 2 * C::STAGE;                        // B packed upper triangles
   int *idxs = reinterpret_cast<int *>(sys + B * C::SYS);  // [B][NS] column indices (padding repeats a real one)
-  float *es = reinterpret_cast<float *>(idxs + C::META); // [B][NS] sqrt(|c| - 1) / 2^14, 0 on padding
-  float *zs = es + C::META;                              // [B][NS] E^-1 c+, then t = E s
+  float *es = reinterpret_cast<float *>(idxs + C::META);  // [B][NS] sqrt(|c| - 1) / 2^14, 0 on padding
+  float *zs = es + C::META;                               // [B][NS] E^-1 c+, then t = E s
   unsigned *badbits = reinterpret_cast<unsigned *>(zs + C::META);
   const bool usable = *whiten_ok != 0;
   const int l = lane % G, sb = lane / G;
@@ -397,21 +425,23 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
     }
 
     // ---- phase A: K = W_u W_u^T for every row of the batch, 16 factor dimensions per phase; the gathers of
-    //      phase p + 1 (possibly the next row's first) are in flight while phase p is multiplied
+    //      phase p + 1 (possibly the next row's first) are in flight while phase p is multiplied.  W arrives
+    //      already split (dense.cu): per row and phase 8 words of fp16 pairs "hi" and 8 words "lo".
     auto issue = [&](int p) {
       const int b = p / NPH, ph = p % NPH;
-      float *st = stage + (p & 1) * C::STAGE;
+      uint32_t *st = stage + (p & 1) * C::STAGE;
       const int *ix = idxs + b * NS;
 #pragma unroll
-      for (int q = 0; q < NG; ++q) {
+      for (int q = 0; q < NT8; ++q) {
         const int ri = ix[8 * q + g];
-        cp_async16(st + (8 * q + g) * LDW + 4 * t, W + (int64_t)ri * F + C::KP * ph + 4 * t);
+        cp_async16(reinterpret_cast<float *>(st + (8 * q + g) * LDW + 4 * t),
+                   reinterpret_cast<const float *>(W + (int64_t)ri * F + C::KP * ph + 4 * t));
       }
       cp_async_commit();
     };
-    float acc[S::NTILES][4];
+    float acc[C::NTILES][4];
 #pragma unroll
-    for (int e = 0; e < S::NTILES; ++e) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
+    for (int e = 0; e < C::NTILES; ++e) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
     const int TP = nb * NPH;
     issue(0);
     for (int p = 0; p < TP; ++p) {
@@ -422,25 +452,30 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
         cp_async_wait<0>();
       }
       __syncwarp();
-      const float *sg = stage + (p & 1) * C::STAGE;
+      const uint32_t *sg = stage + (p & 1) * C::STAGE;
       {
-        uint32_t h0[S::NT8], h1[S::NT8], l0[S::NT8], l1[S::NT8];
+        uint32_t h0[NT8], h1[NT8], l0[NT8], l1[NT8];
 #pragma unroll
-        for (int c = 0; c < S::NT8; ++c) {
-          split_f16x2(*reinterpret_cast<const float2 *>(sg + (8 * c + g) * LDW + 2 * t), h0[c], l0[c]);
-          split_f16x2(*reinterpret_cast<const float2 *>(sg + (8 * c + g) * LDW + 2 * t + 8), h1[c], l1[c]);
+        for (int c = 0; c < NT8; ++c) {
+          const uint32_t *rp = sg + (8 * c + g) * LDW + t;
+          h0[c] = rp[0];   // dims 2t, 2t+1 (hi)
+          h1[c] = rp[4];   // dims 2t+8, 2t+9 (hi)
+          l0[c] = rp[8];   // the same, lo
+          l1[c] = rp[12];
         }
 #pragma unroll
         for (int term = 0; term < 3; ++term) {  // lo * hi, hi * lo, hi * hi: the chain through a tile is a sweep apart
 #pragma unroll
-          for (int i = 0; i < NBs; ++i) {
+          for (int i = 0; i < NM; ++i) {
+            constexpr uint32_t kZero = 0u;
+            const bool second = 2 * i + 1 < NT8;  // compile time after unrolling: rows 16 i + 8 .. exist
             const uint32_t a0 = term == 0 ? l0[2 * i] : h0[2 * i];
-            const uint32_t a1 = term == 0 ? l0[2 * i + 1] : h0[2 * i + 1];
+            const uint32_t a1 = second ? (term == 0 ? l0[2 * i + (second ? 1 : 0)] : h0[2 * i + (second ? 1 : 0)]) : kZero;
             const uint32_t a2 = term == 0 ? l1[2 * i] : h1[2 * i];
-            const uint32_t a3 = term == 0 ? l1[2 * i + 1] : h1[2 * i + 1];
+            const uint32_t a3 = second ? (term == 0 ? l1[2 * i + (second ? 1 : 0)] : h1[2 * i + (second ? 1 : 0)]) : kZero;
 #pragma unroll
-            for (int j = 2 * i; j < S::NT8; ++j) {
-              float(&d)[4] = acc[S::tidx(i, j)];
+            for (int j = 2 * i; j < NT8; ++j) {
+              float(&d)[4] = acc[C::tidx(i, j)];
               if (term == 1) mma_f16(d, a0, a1, a2, a3, l0[j], l1[j]);
               else mma_f16(d, a0, a1, a2, a3, h0[j], h1[j]);
             }
@@ -453,19 +488,20 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
         float *sy = sys + b * C::SYS;
         const float *eb = es + b * NS;
 #pragma unroll
-        for (int i = 0; i < NBs; ++i) {
+        for (int i = 0; i < NM; ++i) {
+          const bool second = 2 * i + 1 < NT8;
           const int r0 = 16 * i + g, r1 = r0 + 8;
-          const float er0 = eb[r0], er1 = eb[r1];
+          const float er0 = eb[r0], er1 = second ? eb[second ? r1 : r0] : 0.f;
           const int ro0 = r0 * NS - ((r0 * (r0 + 1)) >> 1), ro1 = r1 * NS - ((r1 * (r1 + 1)) >> 1);
 #pragma unroll
-          for (int j = 2 * i; j < S::NT8; ++j) {
+          for (int j = 2 * i; j < NT8; ++j) {
             const int c0 = 8 * j + 2 * t, c1 = c0 + 1;
             const float2 ec = *reinterpret_cast<const float2 *>(eb + c0);
-            float(&d)[4] = acc[S::tidx(i, j)];
+            float(&d)[4] = acc[C::tidx(i, j)];
             if (c0 >= r0) sy[ro0 + c0] = fmaf(er0 * ec.x, d[0], r0 == c0 ? 1.f : 0.f);
             if (c1 >= r0) sy[ro0 + c1] = fmaf(er0 * ec.y, d[1], r0 == c1 ? 1.f : 0.f);
-            if (c0 >= r1) sy[ro1 + c0] = fmaf(er1 * ec.x, d[2], r1 == c0 ? 1.f : 0.f);
-            if (c1 >= r1) sy[ro1 + c1] = fmaf(er1 * ec.y, d[3], r1 == c1 ? 1.f : 0.f);
+            if (second && c0 >= r1) sy[ro1 + c0] = fmaf(er1 * ec.x, d[2], r1 == c0 ? 1.f : 0.f);
+            if (second && c1 >= r1) sy[ro1 + c1] = fmaf(er1 * ec.y, d[3], r1 == c1 ? 1.f : 0.f);
             d[0] = d[1] = d[2] = d[3] = 0.f;
           }
         }
@@ -491,7 +527,7 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
       }
     }
     const unsigned notfin = __ballot_sync(kFull, !fin);
-    if (lane < nb && ((notfin >> (lane * G)) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u))))
+    if (lane < nb && ((notfin >> (lane * G)) & ((1u << G) - 1u)))
       my_defer = true;  // cannot happen for finite inputs (M >= I); let the full-size path decide
     if (lane < nb && my_defer) deferred[atomicAdd(n_deferred, 1)] = mine;
     __syncwarp();
@@ -529,12 +565,13 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
   }
 }
 
-template <int NB, int NBs>
-int run_short(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, int64_t count, int slot, cudaStream_t stream) {
-  using C = BatchCfg<NB, NBs>;
+template <int NB, int NS>
+int run_short(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, int64_t end, int slot, cudaStream_t stream) {
+  using C = BatchCfg<NB, NS>;
+  const int64_t count = end - begin;
   if (count <= 0) return ALS_OK;
   const int smem = C::SMEM_FLOATS * (int)sizeof(float);
-  auto kern = short_batch_kernel<NB, NBs>;
+  auto kern = short_batch_kernel<NB, NS>;
   ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int ctas_per_sm = 0;
   ALS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * kBatchWarps, smem));
@@ -543,34 +580,39 @@ int run_short(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, in
     return ALS_E_CUDA;
   }
   const int grid = (int)std::min<int64_t>(ceil_div(count, (int64_t)kBatchWarps * C::B), (int64_t)ctx->sm_count * ctas_per_sm);
-  kern<<<grid, 32 * kBatchWarps, smem, stream>>>(Cm->indices, Cm->data, ctx->whitened, ctx->zfactors, X->d, Cm->row_offset,
-                                                  Cm->work + begin, (int)count, ctx->counters + kCtrShort + slot,
-                                                  ctx->deferred, ctx->counters + kCtrDeferredCount,
-                                                  ctx->counters + kCtrWhitenOk, X->peers_dev, X->n_peers);
+  kern<<<grid, 32 * kBatchWarps, smem, stream>>>(Cm->indices, Cm->data, reinterpret_cast<const uint32_t *>(ctx->whitened),
+                                                  ctx->zfactors, X->d, Cm->row_offset, Cm->work + begin, (int)count,
+                                                  ctx->counters + kCtrShort + slot, ctx->deferred,
+                                                  ctx->counters + kCtrDeferredCount, ctx->counters + kCtrWhitenOk,
+                                                  X->peers_dev, X->n_peers);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
   return ALS_OK;
 }
 
-// items [begin, n_work) split into the classes (32, 48], (16, 32], [0, 16] by the schedule's suffix offsets
+// items [begin, n_work) split into the size classes (40, 48], (32, 40], ... [0, 8] by the schedule's suffix offsets
+// (kShortThresholds); a system of NS unknowns needs NS < F, so a narrower factor matrix stops earlier
 template <int NB>
 int run_short_classes(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t begin, int max_len, cudaStream_t stream) {
-  const int64_t b48 = std::max(begin, Cm->le_begin[0]), b32 = std::max(begin, Cm->le_begin[1]),
-                b16 = std::max(begin, Cm->le_begin[2]);
-  int rc = ALS_OK;
-  if (begin < b48) {
+  int64_t lb[kNumShortThresholds];
+  for (int c = 0; c < kNumShortThresholds; ++c) lb[c] = std::max(begin, Cm->le_begin[c]);
+  if (begin < lb[0]) {
     set_error("short rows: items longer than 48 nonzeros");
     return ALS_E_INVALID;
   }
+  (void)max_len;
+  int rc = ALS_OK;
+  // longest first: the classes with the most work per row start (and spread over the SMs) before the cheap ones
   if constexpr (NB >= 4) {
-    if (max_len > 32) rc = run_short<NB, 3>(ctx, Cm, X, b48, b32 - b48, 0, stream);
-    if (rc != ALS_OK) return rc;
+    if ((rc = run_short<NB, 48>(ctx, Cm, X, lb[0], lb[1], 0, stream)) != ALS_OK) return rc;
+    if ((rc = run_short<NB, 40>(ctx, Cm, X, lb[1], lb[2], 1, stream)) != ALS_OK) return rc;
   }
   if constexpr (NB >= 3) {
-    if (max_len > 16) rc = run_short<NB, 2>(ctx, Cm, X, b32, b16 - b32, 1, stream);
-    if (rc != ALS_OK) return rc;
+    if ((rc = run_short<NB, 32>(ctx, Cm, X, lb[2], lb[3], 2, stream)) != ALS_OK) return rc;
+    if ((rc = run_short<NB, 24>(ctx, Cm, X, lb[3], lb[4], 3, stream)) != ALS_OK) return rc;
   }
-  return run_short<NB, 1>(ctx, Cm, X, b16, Cm->n_work - b16, 2, stream);
+  if ((rc = run_short<NB, 16>(ctx, Cm, X, lb[4], lb[5], 4, stream)) != ALS_OK) return rc;
+  return run_short<NB, 8>(ctx, Cm, X, lb[5], Cm->n_work, 5, stream);
 }
 
 }  // namespace
@@ -593,7 +635,7 @@ int short_rows_prepare(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) 
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
   // 64 padded factors: one pass on the tcgen05 tensor cores (dense.cu); the whiten_fma knob keeps the fp32 FMA tiles
-  if (F == 64 && !ctx->knobs.whiten_fma) return launch_dense_whiten(ctx, Y, stream);
+  if (F == 64 && Y->rows >= 128 && !ctx->knobs.whiten_fma) return launch_dense_whiten(ctx, Y, stream);  // (a TMA box is 128 rows)
   switch (F / 16) {
     case 2: return run_whiten_rows<2>(ctx, Y, stream);
     case 3: return run_whiten_rows<3>(ctx, Y, stream);

@@ -57,6 +57,7 @@ struct als_knobs {
   int short_serial = 0;       // ALS_B200_SHORT_SERIAL: short-row kernels on the compute stream instead of the aux stream
   int whiten_fma = 0;         // ALS_B200_WHITEN_FMA: fp32 FMA tiles for W = Y P, Z = Y G^-1 instead of the tcgen05 apply
   int gramian_mma = 0;        // ALS_B200_GRAMIAN_MMA: legacy mma.sync Gramian
+  int gramian_fma = 0;        // ALS_B200_GRAMIAN_FMA: fp32 FMA Gramian instead of the tcgen05 one (64 padded factors)
   int cg_nv = 2;              // ALS_B200_CG_NV: float4 words per lane of the CG kernel (1 / 2 / 4)
 };
 
@@ -136,8 +137,8 @@ struct als_csr {
   // schedule
   als::WorkItem *work = nullptr;    // main pass: whole rows + chunks, longest first
   int64_t n_work = 0;
-  // work is sorted by length, so the items of at most 48 / 32 / 16 / 0 nonzeros are suffixes: first index of each
-  int64_t le_begin[4] = {0, 0, 0, 0};
+  // work is sorted by length, so the items of at most 48 / 40 / ... / 8 / 0 nonzeros are suffixes: first index of each
+  int64_t le_begin[7] = {0, 0, 0, 0, 0, 0, 0};
   bool sched_pending = false;  // transposed on the device: the schedule is built at first use (ensure_schedule)
   als::WorkItem *finish = nullptr;  // finish pass: one per giant row (row, first slot, #slots)
   int64_t n_finish = 0;
@@ -159,10 +160,12 @@ enum { kProfGramian = 0, kProfCholesky = 1, kProfCholFinish = 2, kProfCg = 3, kP
 
 // slots of als_ctx::counters
 enum {
-  kCtrMain = 0, kCtrFinish = 1, kCtrShort = 2 /* +0..2: one per short class */, kCtrDeferredCount = 5,
-  kCtrDeferredWork = 6, kCtrWhitenOk = 7, kCtrHasNan = 8
+  kCtrMain = 0, kCtrFinish = 1, kCtrDeferredCount = 2, kCtrDeferredWork = 3, kCtrWhitenOk = 4, kCtrHasNan = 5,
+  kCtrShort = 8 /* +0..5: one per short-row size class */
 };
-constexpr int kShortThresholds[4] = {48, 32, 16, 0};  // als_csr::le_begin[i] <-> length <= kShortThresholds[i]
+// size classes of the short-row path: als_csr::le_begin[i] is the first work item of at most kShortThresholds[i] nonzeros
+constexpr int kNumShortThresholds = 7;
+constexpr int kShortThresholds[kNumShortThresholds] = {48, 40, 32, 24, 16, 8, 0};
 
 // Device memory comes from CUDA's stream-ordered pool on ctx->stream with the release threshold lifted, so the
 // arrays of a second fit() are served from what the first one freed (cudaMalloc / cudaFree cost 0.1-1 ms each and
@@ -188,6 +191,8 @@ int launch_cholesky_wide(als_ctx *ctx, const als_csr *C, als_factors *X, const a
 int short_rows_prepare(als_ctx *ctx, const als_factors *Y, cudaStream_t stream);
 // W = Y (2^14 P) and Z = Y G^-1 in one pass on the tcgen05 tensor cores (dense.cu; 64 padded factors)
 int launch_dense_whiten(als_ctx *ctx, const als_factors *Y, cudaStream_t stream);
+// G = Y^T Y on the tcgen05 tensor cores (dense.cu; 64 padded factors, Y of at least one row) -> ctx->G
+int launch_gramian_tc(als_ctx *ctx, const als_factors *Y);
 int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len,
                       cudaStream_t stream);
 int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps);

@@ -14,9 +14,11 @@
 //               accumulators in TMEM, completion signalled with tcgen05.commit;
 //   warps 2-5   split the landed tile in place into its TF32-rounded hi part and the exact remainder lo
 //               (the only SIMT arithmetic), then drain the previous tile's accumulators with tcgen05.ld,
-//               stage them 128B-swizzled in shared memory and hand them to TMA stores.
+//               stage them 128B-swizzled in shared memory (W as fp16 hi / lo pairs, the operand format of the
+//               short-row kernel's mma.sync.m16n8k16; Z as fp32) and hand them to TMA stores.
 // The MMAs of tile t run while the workers drain tile t - 1; the kernel is bound by HBM (96 KB per 128 rows).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.h"
 
@@ -223,6 +225,24 @@ dense_apply_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_const
         if (wt == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         unsigned char *box = gbase + kOffOut + (c & 1) * kBoxBytes;
+        if (c < 2) {
+          // W leaves in the split format the short-row kernel multiplies with (cholesky_short.cu): per 16 dimensions
+          // 8 words of fp16 pairs "hi" and 8 words "lo"; this 32-dimension chunk is two such phases = 128 bytes
+          uint32_t w[32];
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x0 = __uint_as_float(v[16 * pp + 2 * j]), x1 = __uint_as_float(v[16 * pp + 2 * j + 1]);
+              const __half2 h = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h);
+              const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+              w[16 * pp + j] = *reinterpret_cast<const uint32_t *>(&h);
+              w[16 * pp + 8 + j] = *reinterpret_cast<const uint32_t *>(&lo);
+            }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = w[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int pj = j ^ (row & 7);
@@ -277,6 +297,157 @@ __global__ void dense_prepare_b_kernel(const float *__restrict__ Ps, const float
     bt_hi[e] = hi;
     bt_lo[e] = x - hi;
   }
+}
+
+// ---- Gramian G = Y^T Y on tcgen05 (R4; reference: np.dot(Y.T, Y), implicit/cpu/_als.pyx:70,164,268) ----------
+// Both operands of Y^T Y are the SAME shared-memory tile of Y read MN-major (the contraction runs over the rows):
+// A = Y_hi^T (M = 64 factors) and B = [Y_hi | Y_lo] (N = 128), so one tcgen05.mma kind::tf32 per 8 rows yields
+// hi^T hi (columns 0..63) and hi^T lo (columns 64..127) at once; lo^T hi is the transpose of the second block and
+// is added when the partials are reduced: G = S1 + S2 + S2^T (the 3xTF32 split at two thirds of the tensor work).
+// Per CTA: TMA producer (128-row tiles, 2 stages), one MMA-issuing lane, four worker warps that split a landed
+// tile in place into hi (TF32, rounded to nearest) and lo.  The 64 x 128 accumulator stays in TMEM for the whole
+// sweep and is written once, as this CTA's partial; partials are summed in fp64 in a fixed order.
+constexpr int kGramStage = 4 * kBoxBytes;  // [hi cols 0-31 | hi cols 32-63 | lo cols 0-31 | lo cols 32-63], 16 KB each
+constexpr int kGramOffBar = 2 * kGramStage;
+constexpr int kGramSmem = kGramOffBar + 128 + 1024;
+enum { kGFull0 = 0, kGFull1, kGReady0, kGReady1, kGMma0, kGMma1, kGAllDone, kGNumBars };
+
+// MN-major operand, 128B swizzle: 32 floats (128 bytes) of the M/N extent per atom row, 8 rows of K per atom
+// (1024 bytes, SBO between K groups), atoms along M/N are LBO = 16 KB apart (the TMA boxes of a stage)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(kBoxBytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 64, N = 128
+constexpr uint32_t kIdescGram = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+                                ((uint32_t)(64 >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32_idesc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 1)
+gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float *__restrict__ partials) {
+  extern __shared__ unsigned char dense_smem_raw[];
+  const uint32_t raw = smem_u32(dense_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char *gbase = dense_smem_raw + (base - raw);
+  const uint32_t bars = base + kGramOffBar;
+  auto bar = [&](int i) -> uint32_t { return bars + 8u * (uint32_t)i; };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gbase + kGramOffBar + 8 * kGNumBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(kGFull0), 1);
+    mbar_init(bar(kGFull1), 1);
+    mbar_init(bar(kGReady0), 128);
+    mbar_init(bar(kGReady1), 128);
+    mbar_init(bar(kGMma0), 1);
+    mbar_init(bar(kGMma1), 1);
+    mbar_init(bar(kGAllDone), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                 "r"(128)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int t = 0; t < my_tiles; ++t) {
+        const int s = t & 1;
+        if (t >= 2) mbar_wait(bar(kGMma0 + s), (uint32_t)(((t >> 1) - 1) & 1));
+        const int row0 = ((int)blockIdx.x + t * (int)gridDim.x) * kTileM;
+        mbar_expect_tx(bar(kGFull0 + s), 2 * kBoxBytes);
+        tma_load_2d(base + s * kGramStage, &map_y, bar(kGFull0 + s), 0, row0);
+        tma_load_2d(base + s * kGramStage + kBoxBytes, &map_y, bar(kGFull0 + s), 32, row0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t acc = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(bar(kGReady0 + s), (uint32_t)((t >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = base + s * kGramStage;
+#pragma unroll
+        for (int j = 0; j < kTileM / 8; ++j) {  // 8 rows of Y per MMA
+          const uint64_t d = umma_desc_mn_sw128(st + j * 1024);
+          umma_tf32_idesc(tmem_base, d, d, kIdescGram, acc);
+          acc = 1;
+        }
+        umma_commit(bar(kGMma0 + s));
+      }
+      umma_commit(bar(kGAllDone));
+    }
+  } else {
+    const int wt = threadIdx.x - 64;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int s = t & 1;
+      mbar_wait(bar(kGFull0 + s), (uint32_t)((t >> 1) & 1));
+      float4 *a = reinterpret_cast<float4 *>(gbase + s * kGramStage);
+      float4 *alo = reinterpret_cast<float4 *>(gbase + s * kGramStage + 2 * kBoxBytes);
+#pragma unroll 4
+      for (int e = wt; e < 2 * kBoxBytes / 16; e += 128) {
+        float4 hi, lo;
+        split4(a[e], hi, lo);
+        a[e] = hi;
+        alo[e] = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar(kGReady0 + s));
+    }
+    // the 64 x 128 accumulator: rows 16 q .. 16 q + 15 live in lanes 32 q .. 32 q + 15 (M = 64 uses half of every
+    // 32-lane quarter), so lanes 0..15 of each worker warp hold one row each
+    mbar_wait(bar(kGAllDone), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;
+    float *dst = partials + ((size_t)blockIdx.x * 64 + 16 * quarter + lane) * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(32 * c), v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4 *>(dst + 32 * c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+  }
+}
+
+// G[i][j] = sum over CTAs of S1[i][j] + S2[i][j] + S2[j][i], in fp64, CTAs in index order
+__global__ void __launch_bounds__(256) gramian_tc_reduce_kernel(const float *__restrict__ partials, int nparts, float *__restrict__ G) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 64 * 64) return;
+  const int i = e >> 6, j = e & 63;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    const float *P = partials + (size_t)p * 64 * 128;
+    s += (double)P[i * 128 + j] + ((double)P[i * 128 + 64 + j] + (double)P[j * 128 + 64 + i]);
+  }
+  G[e] = (float)s;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -345,6 +516,34 @@ int launch_dense_whiten(als_ctx *ctx, const als_factors *Y, cudaStream_t stream)
   dense_apply_kernel<<<grid, kDenseThreads, kDenseSmem, stream>>>(my, mbh, mbl, mw, mz, n_tiles);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
+  return ALS_OK;
+}
+
+// G = Y^T Y for a 64-wide Y on the tcgen05 tensor cores -> ctx->G (the caller regularises)
+int launch_gramian_tc(als_ctx *ctx, const als_factors *Y) {
+  const int64_t rows = std::max<int64_t>(Y->rows, 1);
+  const int n_tiles = (int)ceil_div(rows, kTileM);
+  const int grid = std::min(n_tiles, ctx->sm_count);
+  const int64_t need = (int64_t)grid * 64 * 128;
+  if (need > ctx->gram_partials_cap) {
+    if (ctx->gram_partials) {
+      ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+      ALS_CUDA(cudaFree(ctx->gram_partials));
+      ctx->gram_partials = nullptr;
+    }
+    const int64_t cap = (int64_t)ctx->sm_count * 2 * 128 * 128;
+    ALS_CUDA(cudaMalloc(&ctx->gram_partials, sizeof(float) * cap));
+    ctx->gram_partials_cap = cap;
+  }
+  CUtensorMap my;
+  int rc = make_map(&my, Y->d, rows);
+  if (rc != ALS_OK) return rc;
+  ALS_CUDA(cudaFuncSetAttribute(gramian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
+  gramian_tc_kernel<<<grid, kDenseThreads, kGramSmem, ctx->stream>>>(my, n_tiles, ctx->gram_partials);
+  ALS_CUDA(cudaGetLastError());
+  gramian_tc_reduce_kernel<<<16, 256, 0, ctx->stream>>>(ctx->gram_partials, grid, ctx->G);
+  ALS_CUDA(cudaGetLastError());
+  ctx->launches += 2;
   return ALS_OK;
 }
 
