@@ -95,6 +95,11 @@ class AlternatingLeastSquares:
             else:
                 self._item_factors = host
             self._host_fresh[side] = True
+        if host is not None and host.flags.writeable:
+            # the device replica is refreshed only by assignment (model.item_factors = new): an in-place edit of the
+            # returned array would silently leave recommend / similar_items on the old factors, so it fails loudly
+            host = host.view()
+            host.setflags(write=False)
         return host
 
     def _set_host(self, side, value):
@@ -152,6 +157,12 @@ class AlternatingLeastSquares:
         log.debug("Uploaded and transposed in %.3fs", time.time() - s)
 
         # cpu/als.py:144-147: pre-set factors are kept, otherwise rng.random(...) * 0.01
+        if self.process_group is not None and self.process_group.world > 1 and \
+                (self._get_host("user") is None or self._get_host("item") is None):
+            # every rank must start from the same replicas: rank 0 draws a seed, everyone initialises from it
+            seed = int(random_state.integers(1, 2**31 - 1)) if self.process_group.rank == 0 else 0
+            seed = int(ctx.allreduce([float(seed)], "max")[0])
+            random_state = np.random.default_rng(seed)
         if self._get_host("user") is None:
             self._set_host("user", random_state.random((users, self.factors), dtype=np.float32) * np.float32(0.01))
         if self._get_host("item") is None:
@@ -212,6 +223,12 @@ class AlternatingLeastSquares:
                     ctx.sync()
                     callback(iteration, time.time() - s, loss)
             ctx.sync()
+        except BaseException:
+            if self._p2p:  # failures are raised on every rank in the same half (_raise_together): unmap and leave
+                ctx.detach_peers(X)
+                ctx.detach_peers(Y)
+                self._p2p = False
+            raise
         finally:
             if progress is not None:
                 progress.close()
@@ -238,17 +255,38 @@ class AlternatingLeastSquares:
         all-reduce of the NEXT Gramian -- over the rows this rank just solved -- doubles as the barrier that
         orders the next half after every peer's stores.  Nothing blocks the host."""
         ctx = self.ctx
+        err = None
         if splits is not None and self._p2p:
             rank = self.process_group.rank
-            _lib.half_pregram(ctx, C, X, Y, self.regularization, self.use_cg, self.cg_steps)
+            try:
+                _lib.half_pregram(ctx, C, X, Y, self.regularization, self.use_cg, self.cg_steps)
+            except (ValueError, _lib.AlsError) as e:  # e.g. a row of THIS shard is not positive definite
+                err = e
+            # every rank takes part in the collectives of this half whatever happened locally, then all of them learn
+            # whether any rank failed and raise together (a rank that simply left would hang its peers in NCCL)
             _lib.gramian_shard(ctx, X, splits[rank], splits[rank + 1] - splits[rank])
+            self._raise_together(err)
             return
-        if self.use_cg:
-            _lib.least_squares_cg(ctx, C, X, Y, self.regularization, self.cg_steps)
-        else:
-            _lib.least_squares(ctx, C, X, Y, self.regularization)
+        try:
+            if self.use_cg:
+                _lib.least_squares_cg(ctx, C, X, Y, self.regularization, self.cg_steps)
+            else:
+                _lib.least_squares(ctx, C, X, Y, self.regularization)
+        except (ValueError, _lib.AlsError) as e:
+            if splits is None:
+                raise
+            err = e
         if splits is not None:
             ctx.allgather_rows(X, splits)
+            self._raise_together(err)
+
+    def _raise_together(self, err):
+        """Multi-GPU: all ranks agree on failure (max-reduce of a flag) and raise in the same half-iteration."""
+        failed = self.ctx.allreduce([1.0 if err is not None else 0.0], "max")[0] > 0
+        if err is not None:
+            raise err
+        if failed:
+            raise _lib.AlsError("another rank failed in this half-iteration (see its error message)")
 
     def _loss(self, C, X, Y, users, items, nnz):
         ctx = self.ctx

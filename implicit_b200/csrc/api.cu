@@ -94,9 +94,11 @@ int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr) {
   std::vector<int32_t> owner;
   items.reserve((size_t)csr->rows + 64);
   int64_t slots = 0;
+  csr->max_row_nnz = 0;
   for (int64_t r = 0; r < csr->rows; ++r) {
     const int32_t b = indptr[r], e = indptr[r + 1];
     const int32_t n = e - b;
+    csr->max_row_nnz = std::max<int64_t>(csr->max_row_nnz, n);
     if (n > kSplitNnz) {
       const int32_t nchunks = (int32_t)ceil_div(n, kChunkNnz);
       fin.push_back(WorkItem{(int32_t)r, (int32_t)slots, nchunks, -2});
@@ -238,7 +240,7 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   {
     struct { const char *env; const char *name; } table[] = {
         {"ALS_B200_SHORT_MAX", "short_max"}, {"ALS_B200_SHORT_SERIAL", "short_serial"}, {"ALS_B200_WHITEN_FMA", "whiten_fma"},
-        {"ALS_B200_GRAMIAN_MMA", "gramian_mma"}, {"ALS_B200_GRAMIAN_FMA", "gramian_fma"}, {"ALS_B200_CG_NV", "cg_nv"}};
+        {"ALS_B200_GRAMIAN_MMA", "gramian_mma"}, {"ALS_B200_GRAMIAN_FMA", "gramian_fma"}, {"ALS_B200_TOPK_LEGACY", "topk_legacy"}, {"ALS_B200_CG_NV", "cg_nv"}};
     for (const auto &t : table) {
       const char *e = getenv(t.env);
       if (!e) continue;
@@ -287,6 +289,7 @@ ALS_API int als_ctx_set_knob(als_ctx *ctx, const char *name, int value) {
   else if (!strcmp(name, "whiten_fma")) k.whiten_fma = value != 0;
   else if (!strcmp(name, "gramian_mma")) k.gramian_mma = value != 0;
   else if (!strcmp(name, "gramian_fma")) k.gramian_fma = value != 0;
+  else if (!strcmp(name, "topk_legacy")) k.topk_legacy = value != 0;
   else if (!strcmp(name, "cg_nv")) {
     ALS_REQUIRE(value == 1 || value == 2 || value == 4, "als_ctx_set_knob: cg_nv must be 1, 2 or 4");
     k.cg_nv = value;

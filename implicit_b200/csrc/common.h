@@ -57,6 +57,7 @@ struct als_knobs {
   int short_serial = 0;       // ALS_B200_SHORT_SERIAL: short-row kernels on the compute stream instead of the aux stream
   int whiten_fma = 0;         // ALS_B200_WHITEN_FMA: fp32 FMA tiles for W = Y P, Z = Y G^-1 instead of the tcgen05 apply
   int gramian_mma = 0;        // ALS_B200_GRAMIAN_MMA: legacy mma.sync Gramian
+  int topk_legacy = 0;        // ALS_B200_TOPK_LEGACY: mma.sync top-k kernel for every call (no tcgen05 path)
   int gramian_fma = 0;        // ALS_B200_GRAMIAN_FMA: fp32 FMA Gramian instead of the tcgen05 one (64 padded factors)
   int cg_nv = 2;              // ALS_B200_CG_NV: float4 words per lane of the CG kernel (1 / 2 / 4)
 };
@@ -139,6 +140,7 @@ struct als_csr {
   int64_t n_work = 0;
   // work is sorted by length, so the items of at most 48 / 40 / ... / 8 / 0 nonzeros are suffixes: first index of each
   int64_t le_begin[7] = {0, 0, 0, 0, 0, 0, 0};
+  int64_t max_row_nnz = 0;     // longest row (known once the schedule is built)
   bool sched_pending = false;  // transposed on the device: the schedule is built at first use (ensure_schedule)
   als::WorkItem *finish = nullptr;  // finish pass: one per giant row (row, first slot, #slots)
   int64_t n_finish = 0;
@@ -198,6 +200,12 @@ int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_
 int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps);
 int launch_loss(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y, float reg,
                 double *loss);
+// tcgen05 path of the fused top-k (topk_tc.cu): 64 padded factors, k <= 16, large query batches, no item norms
+bool topk_tc_eligible(int ld, int64_t n_query, int64_t n_items, int k, bool has_norms);
+int64_t topk_tc_scratch_bytes(int64_t n_query, int64_t n_items);
+int launch_topk_tc(als_ctx *ctx, const float *items, int64_t n_items, const float *queries, const int32_t *query_rows,
+                   int64_t n_query, int k, const uint8_t *mask, const int32_t *liked_indptr, const int32_t *liked_indices,
+                   int32_t *out_ids, float *out_scores, void *scratch);
 int launch_topk(als_ctx *ctx, const als_factors *items, const als_factors *queries, const int32_t *query_rows,
                 int64_t n_query, int k, const float *item_norms_host, const als_csr *liked,
                 const int32_t *filter_items, int64_t n_filter, int32_t *ids_host, float *scores_host);

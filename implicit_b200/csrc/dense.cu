@@ -300,26 +300,24 @@ __global__ void dense_prepare_b_kernel(const float *__restrict__ Ps, const float
 }
 
 // ---- Gramian G = Y^T Y on tcgen05 (R4; reference: np.dot(Y.T, Y), implicit/cpu/_als.pyx:70,164,268) ----------
-// Both operands of Y^T Y are the SAME shared-memory tile of Y read MN-major (the contraction runs over the rows):
-// A = Y_hi^T (M = 64 factors) and B = [Y_hi | Y_lo] (N = 128), so one tcgen05.mma kind::tf32 per 8 rows yields
-// hi^T hi (columns 0..63) and hi^T lo (columns 64..127) at once; lo^T hi is the transpose of the second block and
-// is added when the partials are reduced: G = S1 + S2 + S2^T (the 3xTF32 split at two thirds of the tensor work).
-// Per CTA: TMA producer (128-row tiles, 2 stages), one MMA-issuing lane, four worker warps that split a landed
-// tile in place into hi (TF32, rounded to nearest) and lo.  The 64 x 128 accumulator stays in TMEM for the whole
-// sweep and is written once, as this CTA's partial; partials are summed in fp64 in a fixed order.
-constexpr int kGramStage = 4 * kBoxBytes;  // [hi cols 0-31 | hi cols 32-63 | lo cols 0-31 | lo cols 32-63], 16 KB each
-constexpr int kGramOffBar = 2 * kGramStage;
+// The contraction runs over the ROWS of Y, so both operands are the transposed tile.  The worker warps, which have
+// to touch every element anyway for the TF32 hi / lo split, write the split halves TRANSPOSED into a K-major,
+// 128B-swizzled operand tile T = [hi^T ; lo^T] (128 operand rows = 64 factors hi + 64 factors lo, K = the 128 rows of
+// the landed Y tile): A = hi^T (M = 64) and B = T (N = 128) start at the same address, and one tcgen05.mma
+// kind::tf32 per 8 rows of Y yields hi^T hi (columns 0..63) and hi^T lo (columns 64..127) at once; lo^T hi is the
+// transpose of the second block and is added when the partials are reduced: G = S1 + S2 + S2^T (the 3xTF32 split
+// at two thirds of the tensor work).  Per CTA: TMA producer (128-row tiles, 2 stages), one MMA-issuing lane, four
+// worker warps.  The 64 x 128 accumulator stays in TMEM for the whole sweep and is written once, as this CTA's
+// partial; partials are summed in fp64 in a fixed order.
+constexpr int kGramRaw = 2 * kBoxBytes;           // a landed Y tile: cols 0-31 | cols 32-63
+constexpr int kGramT = 4 * kBoxBytes;             // [128 operand rows][128 K] as 4 K-chunks of 32
+constexpr int kGramOffT = 2 * kGramRaw;           // after the 2 raw stages
+constexpr int kGramOffBar = kGramOffT + 2 * kGramT;
 constexpr int kGramSmem = kGramOffBar + 128 + 1024;
-enum { kGFull0 = 0, kGFull1, kGReady0, kGReady1, kGMma0, kGMma1, kGAllDone, kGNumBars };
+enum { kGFull0 = 0, kGFull1, kGRawFree0, kGRawFree1, kGReady0, kGReady1, kGMma0, kGMma1, kGAllDone, kGNumBars };
 
-// MN-major operand, 128B swizzle: 32 floats (128 bytes) of the M/N extent per atom row, 8 rows of K per atom
-// (1024 bytes, SBO between K groups), atoms along M/N are LBO = 16 KB apart (the TMA boxes of a stage)
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(kBoxBytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 64, N = 128
-constexpr uint32_t kIdescGram = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
-                                ((uint32_t)(64 >> 4) << 24);
+// kind::tf32, fp32 accumulate, A and B K-major, M = 64, N = 128
+constexpr uint32_t kIdescGram = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32_idesc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -347,6 +345,8 @@ gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float 
   if (threadIdx.x == 0) {
     mbar_init(bar(kGFull0), 1);
     mbar_init(bar(kGFull1), 1);
+    mbar_init(bar(kGRawFree0), 128);
+    mbar_init(bar(kGRawFree1), 128);
     mbar_init(bar(kGReady0), 128);
     mbar_init(bar(kGReady1), 128);
     mbar_init(bar(kGMma0), 1);
@@ -369,11 +369,11 @@ gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float 
     if (lane == 0) {
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
-        if (t >= 2) mbar_wait(bar(kGMma0 + s), (uint32_t)(((t >> 1) - 1) & 1));
+        if (t >= 2) mbar_wait(bar(kGRawFree0 + s), (uint32_t)(((t >> 1) - 1) & 1));  // the workers have read raw stage s
         const int row0 = ((int)blockIdx.x + t * (int)gridDim.x) * kTileM;
-        mbar_expect_tx(bar(kGFull0 + s), 2 * kBoxBytes);
-        tma_load_2d(base + s * kGramStage, &map_y, bar(kGFull0 + s), 0, row0);
-        tma_load_2d(base + s * kGramStage + kBoxBytes, &map_y, bar(kGFull0 + s), 32, row0);
+        mbar_expect_tx(bar(kGFull0 + s), kGramRaw);
+        tma_load_2d(base + s * kGramRaw, &map_y, bar(kGFull0 + s), 0, row0);
+        tma_load_2d(base + s * kGramRaw + kBoxBytes, &map_y, bar(kGFull0 + s), 32, row0);
       }
     }
   } else if (warp == 1) {
@@ -383,10 +383,10 @@ gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float 
         const int s = t & 1;
         mbar_wait(bar(kGReady0 + s), (uint32_t)((t >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = base + s * kGramStage;
+        const uint32_t T = base + kGramOffT + s * kGramT;
 #pragma unroll
-        for (int j = 0; j < kTileM / 8; ++j) {  // 8 rows of Y per MMA
-          const uint64_t d = umma_desc_mn_sw128(st + j * 1024);
+        for (int ks = 0; ks < kTileM / 8; ++ks) {  // 8 rows of Y (the K extent of a tf32 MMA) per instruction
+          const uint64_t d = umma_desc_k_sw128(T + (uint32_t)((ks >> 2) * kBoxBytes + (ks & 3) * 32));
           umma_tf32_idesc(tmem_base, d, d, kIdescGram, acc);
           acc = 1;
         }
@@ -395,37 +395,48 @@ gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float 
       umma_commit(bar(kGAllDone));
     }
   } else {
-    const int wt = threadIdx.x - 64;
+    // ===== workers: split + transpose the landed tile into the operand tile =====
+    const int w4 = warp & 3;               // K-chunk of the operand tile = rows 32 w4 .. 32 w4 + 31 of the Y tile
+    const int r = 32 * w4 + lane;          // this lane's row of the Y tile
     for (int t = 0; t < my_tiles; ++t) {
       const int s = t & 1;
       mbar_wait(bar(kGFull0 + s), (uint32_t)((t >> 1) & 1));
-      float4 *a = reinterpret_cast<float4 *>(gbase + s * kGramStage);
-      float4 *alo = reinterpret_cast<float4 *>(gbase + s * kGramStage + 2 * kBoxBytes);
+      if (t >= 2) mbar_wait(bar(kGMma0 + s), (uint32_t)(((t >> 1) - 1) & 1));  // the MMAs of tile t - 2 have read T[s]
+      const unsigned char *src = gbase + s * kGramRaw;
+      unsigned char *dst = gbase + kGramOffT + s * kGramT + w4 * kBoxBytes;
 #pragma unroll 4
-      for (int e = wt; e < 2 * kBoxBytes / 16; e += 128) {
+      for (int c4 = 0; c4 < 16; ++c4) {
+        // 4 consecutive columns of row r: the 16-byte chunk (c4 % 8) of box (c4 / 8), swizzled with r % 8
+        const float4 x = *reinterpret_cast<const float4 *>(src + (c4 >> 3) * kBoxBytes + r * 128 + (((c4 & 7) ^ (r & 7)) << 4));
         float4 hi, lo;
-        split4(a[e], hi, lo);
-        a[e] = hi;
-        alo[e] = lo;
+        split4(x, hi, lo);
+        const float h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = 4 * c4 + i;  // operand row c (hi) / 64 + c (lo); K index within the chunk = lane
+          const int off = (((lane >> 2) ^ (c & 7)) << 4) + ((lane & 3) << 2);  // (64 + c) % 8 == c % 8
+          *reinterpret_cast<float *>(dst + c * 128 + off) = h[i];
+          *reinterpret_cast<float *>(dst + (64 + c) * 128 + off) = l[i];
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar(kGReady0 + s));
+      mbar_arrive(bar(kGRawFree0 + s));
     }
     // the 64 x 128 accumulator: rows 16 q .. 16 q + 15 live in lanes 32 q .. 32 q + 15 (M = 64 uses half of every
     // 32-lane quarter), so lanes 0..15 of each worker warp hold one row each
     mbar_wait(bar(kGAllDone), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int quarter = warp & 3;
-    float *dst = partials + ((size_t)blockIdx.x * 64 + 16 * quarter + lane) * 128;
+    float *out = partials + ((size_t)blockIdx.x * 64 + 16 * w4 + lane) * 128;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(32 * c), v);
+      tmem_ld32(tmem_base + ((uint32_t)(32 * w4) << 16) + (uint32_t)(32 * c), v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (lane < 16) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4 *>(dst + 32 * c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          *reinterpret_cast<uint4 *>(out + 32 * c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     }
   }

@@ -401,6 +401,12 @@ int launch_topk(als_ctx *ctx, const als_factors *items, const als_factors *queri
   const int64_t o_nrm = take(item_norms_host ? I * 4 : 0);
   const int64_t o_mask = take(n_filter ? I : 0);
   const int64_t o_fl = take(n_filter * 4);
+  // Large batches at 64 padded factors go to the tcgen05 kernel (topk_tc.cu).  It skips filtered items instead of
+  // keeping them at -FLT_MAX, which is the same thing as long as every row has k unfiltered items left.
+  const bool use_tc = !ctx->knobs.topk_legacy && topk_tc_eligible(items->ld, n_query, I, k_eff, item_norms_host != nullptr) &&
+                      (!liked || !liked->sched_pending) &&
+                      I - n_filter - (liked ? liked->max_row_nnz : 0) >= k_eff;
+  const int64_t o_tc = take(use_tc ? topk_tc_scratch_bytes(n_query, I) : 0);
   int rc = ensure_scratch(ctx, off);
   if (rc != ALS_OK) return rc;
   char *base = (char *)ctx->scratch;
@@ -442,6 +448,10 @@ int launch_topk(als_ctx *ctx, const als_factors *items, const als_factors *queri
   a.ids = (int32_t *)(base + o_ids);
   a.scores = (float *)(base + o_sc);
 #define CALL(FF) run_topk_f<FF>(ctx, a)
+  if (use_tc) {
+    rc = launch_topk_tc(ctx, a.items, I, a.queries, a.query_rows, n_query, k_eff, a.mask, a.liked_indptr, a.liked_indices,
+                        a.ids, a.scores, base + o_tc);
+  } else
   switch (items->ld / 16) {
     case 1: rc = CALL(16); break;
     case 2: rc = CALL(32); break;

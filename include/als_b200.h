@@ -57,7 +57,7 @@ int als_device_count(void);
 int als_ctx_create(int device, als_ctx **out);
 int als_ctx_destroy(als_ctx *ctx);
 
-/* Measurement knobs ("short_max" 0/16/32/48, "short_serial", "whiten_fma", "gramian_mma", "gramian_fma", "cg_nv" 1/2/4).  The
+/* Measurement knobs ("short_max" 0/16/32/48, "short_serial", "whiten_fma", "gramian_mma", "gramian_fma", "topk_legacy", "cg_nv" 1/2/4).  The
  * environment variables ALS_B200_<KNOB> are read once, in als_ctx_create, and reported on stderr when set; this
  * call changes a knob afterwards (A/B tools).  Results do not depend on any knob beyond fp32 rounding.
  * (No reference equivalent.) */

@@ -197,3 +197,57 @@ def test_least_squares_with_gramian_matches_reference(lib, ctx, orc, f):
     e = row_err(got, exp)
     print(f"with_gramian f={f}: max {e.max():.2e} median {np.median(e):.2e}")
     assert e.max() < CHOL_MAX
+
+
+# ---------------------------------------------------------------------------------------- tcgen05 top-k at mid size
+@pytest.mark.parametrize("k", [1, 10, 16])
+def test_topk_tcgen05_path_matches_oracle_and_legacy_kernel(lib, ctx, orc, k):
+    """The tcgen05 kernel (csrc/topk_tc.cu: batches of >= 1024 queries, 64 factors, k <= 16) against the reference's
+    topk and against the mma.sync kernel (knob topk_legacy), with a liked CSR, a global filter list, a ragged last
+    query tile and a ragged last item tile."""
+    Q, I, f = 3000 + 37, 5000 + 113, 64
+    rng = np.random.default_rng(100 + k)
+    users = rng.standard_normal((Q, f), dtype=np.float32) * np.float32(0.3)
+    items = rng.standard_normal((I, f), dtype=np.float32) * np.float32(0.3)
+    liked = synthetic.power_law_csr(Q, I, 25 * Q, 9)
+    flt = np.sort(rng.choice(I, 200, replace=False)).astype(np.int32)
+    di, dq = lib.DeviceFactors.from_host(ctx, items), lib.DeviceFactors.from_host(ctx, users)
+    dl = lib.DeviceCSR.upload(ctx, liked)
+    ids, sc = lib.topk(ctx, di, dq, k, liked=dl, filter_items=flt)
+    ctx.set_knob("topk_legacy", 1)
+    ids_old, sc_old = lib.topk(ctx, di, dq, k, liked=dl, filter_items=flt)
+    ctx.set_knob("topk_legacy", 0)
+    # a row subset through query_rows (the recommend() path)
+    rows = np.sort(rng.choice(Q, 1500, replace=False)).astype(np.int32)
+    dl2 = lib.DeviceCSR.upload(ctx, liked[rows])
+    ids_r, sc_r = lib.topk(ctx, di, dq, k, query_rows=rows, liked=dl2)
+    for h in (dl2, dl, dq, di):
+        h.close()
+    eids, esc = orc.topk(items, users, k, filter_query_items=liked, filter_items=flt)
+    same = ids == eids
+    noise = 4 * np.finfo(np.float32).eps * np.linalg.norm(users, axis=1)[:, None] * np.linalg.norm(items, axis=1).max()
+    bad = (~same) & (np.abs(sc - esc) > noise)
+    print(f"tcgen05 top-k k={k}: ids equal to the reference {same.mean():.6f} (true mismatches {bad.sum()}), to the mma.sync kernel "
+          f"{(ids == ids_old).mean():.6f}; score rel err {np.abs(sc - esc).max() / np.abs(esc).max():.2e}")
+    assert bad.sum() == 0 and same.mean() > 0.999
+    np.testing.assert_allclose(sc, esc, rtol=2e-5, atol=1e-6)
+    assert (ids == ids_old).mean() > 0.999
+    e2, s2 = orc.topk(items, users[rows], k, filter_query_items=liked[rows])
+    assert (ids_r == e2).mean() > 0.999
+    np.testing.assert_allclose(sc_r, s2, rtol=2e-5, atol=1e-6)
+
+
+def test_topk_tcgen05_exact_ties_follow_select_h(lib, ctx, orc):
+    """Integer-valued factors make every score exact, so ties are real: ids must equal the reference's bit for bit
+    (select.h: at the k-th-score boundary the smaller column wins; equal scores come out larger column first)."""
+    Q, I, f, k = 2048, 4096, 64, 10
+    rng = np.random.default_rng(7)
+    users = rng.integers(-2, 3, size=(Q, f)).astype(np.float32)
+    items = rng.integers(-2, 3, size=(I, f)).astype(np.float32)
+    di, dq = lib.DeviceFactors.from_host(ctx, items), lib.DeviceFactors.from_host(ctx, users)
+    ids, sc = lib.topk(ctx, di, dq, k)
+    dq.close()
+    di.close()
+    eids, esc = orc.topk(items, users, k)
+    np.testing.assert_array_equal(sc, esc)
+    np.testing.assert_array_equal(ids, eids)

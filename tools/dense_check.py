@@ -21,8 +21,16 @@ for rows, kind in ((1000, "normal"), (300000, "cold"), (360037, "normal")):
         return np.abs(a - b).max() / np.abs(b).max(), np.median(np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1))
     ew, ez = err(W, Wt), err(Z, Zt)
     print(f"rows {rows} ({kind}): W max-rel {ew[0]:.2e} row-median {ew[1]:.2e} | Z max-rel {ez[0]:.2e} row-median {ez[1]:.2e} | cond(G) {np.linalg.cond(G):.1e}", flush=True)
-    ctx.sync(); t0 = time.perf_counter()
-    for _ in range(5):
-        _lib.whitened_factors  # timing below uses the half-iteration profile instead
+    Gt = Y64.T @ Y64
+    for knob, name in ((0, "tcgen05"), (1, "fma")):
+        ctx.set_knob("gramian_fma", knob)
+        Gg = _lib.gramian(ctx, Y)
+        ctx.profile(True); ctx.profile_read()
+        for _ in range(5):
+            _lib.gramian(ctx, Y)
+        p = ctx.profile_read(); ctx.profile(False)
+        print(f"   gramian {name}: max-rel {np.abs(Gg - Gt).max() / np.abs(Gt).max():.2e}, asymmetry {np.abs(Gg - Gg.T).max() / np.abs(Gt).max():.1e}, "
+              f"{p['gramian'][0] / 5 * 1e3:.1f} us per call = {rows * 256 / (p['gramian'][0] / 5 * 1e-3) / 1e9:.0f} GB/s", flush=True)
+    ctx.set_knob("gramian_fma", 0)
     del Y
 print("DENSE_CHECK done")
