@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libals_b200.so")
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-ccbin", "/usr/bin/g++"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

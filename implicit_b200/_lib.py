@@ -60,6 +60,8 @@ SIGNATURES = {
     "als_least_squares": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
     "als_least_squares_with_gramian": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
     "als_gramian_shard": (c_int, [c_void_p, c_void_p, c_i64, c_i64]),
+    "als_least_squares_pregram_async": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f64]),
+    "als_solver_status": (c_int, [c_void_p, P(c_i64), P(c_int)]),
     "als_whitened_factors": (c_int, [c_void_p, c_void_p, c_f64, c_void_p, c_void_p]),
     "als_least_squares_pregram": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f64, P(c_i64)]),
     "als_least_squares_cg_pregram": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_int]),
@@ -419,6 +421,25 @@ def whitened_factors(ctx, Y, regularization):
 def gramian_shard(ctx, Y, row0, nrows):
     """Gramian over this rank's rows of Y, summed across ranks, left on the device for the *_pregram solves."""
     check(ctx.lib.als_gramian_shard(ctx.h, Y.h, int(row0), int(nrows)))
+
+
+def half_pregram_async(ctx, Cui, X, Y, regularization, use_cg, cg_steps=3):
+    """half_pregram without the host round trip: failures surface in solver_status()."""
+    if use_cg:
+        check(ctx.lib.als_least_squares_cg_pregram(ctx.h, Cui.h, X.h, Y.h, float(regularization), int(cg_steps)))
+    else:
+        check(ctx.lib.als_least_squares_pregram_async(ctx.h, Cui.h, X.h, Y.h, float(regularization)))
+
+
+def solver_status(ctx):
+    """Synchronises; raises ValueError for a bad row of this rank, AlsError when another rank failed."""
+    bad, anyf = c_i64(-1), c_int(0)
+    rc = ctx.lib.als_solver_status(ctx.h, ctypes.byref(bad), ctypes.byref(anyf))
+    if rc == ALS_E_NOT_POSDEF:
+        raise ValueError("cholesky failed on row %i. Try increasing the regularization parameter." % bad.value)
+    check(rc)
+    if anyf.value:
+        raise AlsError("another rank failed in this iteration (see its error message)")
 
 
 def half_pregram(ctx, Cui, X, Y, regularization, use_cg, cg_steps=3):

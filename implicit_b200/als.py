@@ -207,6 +207,8 @@ class AlternatingLeastSquares:
                 s = time.time()
                 self._half(Cui_s, X, Y, usplit)
                 self._half(Ciu_s, Y, X, isplit)
+                if self._p2p and not self.use_cg:
+                    _lib.solver_status(ctx)  # raises on every rank in the same iteration if any rank's half failed
                 if progress is not None:
                     progress.update(1)
                 if self.calculate_training_loss:
@@ -258,14 +260,10 @@ class AlternatingLeastSquares:
         err = None
         if splits is not None and self._p2p:
             rank = self.process_group.rank
-            try:
-                _lib.half_pregram(ctx, C, X, Y, self.regularization, self.use_cg, self.cg_steps)
-            except (ValueError, _lib.AlsError) as e:  # e.g. a row of THIS shard is not positive definite
-                err = e
-            # every rank takes part in the collectives of this half whatever happened locally, then all of them learn
-            # whether any rank failed and raise together (a rank that simply left would hang its peers in NCCL)
+            # queued, not awaited: a row that is not positive definite is remembered on the device and flagged to every
+            # rank through the Gramian all-reduce; fit() asks for the status once per iteration, on all ranks alike
+            _lib.half_pregram_async(ctx, C, X, Y, self.regularization, self.use_cg, self.cg_steps)
             _lib.gramian_shard(ctx, X, splits[rank], splits[rank + 1] - splits[rank])
-            self._raise_together(err)
             return
         try:
             if self.use_cg:

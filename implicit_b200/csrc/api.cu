@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 
 #include "common.h"
 
@@ -82,6 +83,65 @@ int ensure_pinned(als_ctx *ctx, int64_t bytes) {
   int64_t cap = std::max<int64_t>(bytes, 1 << 20);
   ALS_CUDA(cudaMallocHost(&ctx->pinned, cap));
   ctx->pinned_bytes = cap;
+  return ALS_OK;
+}
+
+
+// ---- host -> device copies of ordinary (pageable) memory ---------------------------------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the driver through one thread at ~12 GB/s; a user of the
+// reference hands fit() ordinary numpy / scipy arrays, so for large buffers four host threads copy 4 MB chunks into
+// page-locked staging buffers of their own and push them over PCIe on their own streams (memcpy and DMA overlap).
+// Page-locked sources take the plain asynchronous copy.
+static constexpr int kStageThreads = 4;
+static constexpr size_t kStageChunk = 4u << 20;
+
+static int h2d_copy(als_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return ALS_OK;
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // an unregistered host pointer may leave an error behind on older drivers
+  if (pinned || bytes < 2 * kStageChunk * kStageThreads) {
+    ALS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ALS_OK;
+  }
+  if (!ctx->stage_buf) {
+    ALS_CUDA(cudaMallocHost(&ctx->stage_buf, kStageThreads * 2 * kStageChunk));
+    for (int t = 0; t < kStageThreads; ++t) {
+      ALS_CUDA(cudaStreamCreateWithFlags(&ctx->stage_stream[t], cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) ALS_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[t][b], cudaEventDisableTiming));
+    }
+    ALS_CUDA(cudaEventCreateWithFlags(&ctx->stage_ready, cudaEventDisableTiming));
+  }
+  // the destination was allocated (stream-ordered) on the compute stream: the staging streams start after it
+  ALS_CUDA(cudaEventRecord(ctx->stage_ready, ctx->stream));
+  for (int t = 0; t < kStageThreads; ++t) ALS_CUDA(cudaStreamWaitEvent(ctx->stage_stream[t], ctx->stage_ready, 0));
+  const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+  std::vector<int> status(kStageThreads, (int)cudaSuccess);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < kStageThreads; ++t) {
+    pool.emplace_back([=, &status]() {
+      cudaSetDevice(ctx->device);
+      cudaError_t e = cudaSuccess;
+      int use = 0;
+      for (size_t c = t; c < nchunks && e == cudaSuccess; c += kStageThreads, ++use) {
+        const int b = use & 1;
+        char *stage = (char *)ctx->stage_buf + ((size_t)t * 2 + b) * kStageChunk;
+        if (use >= 2) e = cudaEventSynchronize(ctx->stage_ev[t][b]);  // the DMA out of this buffer has finished
+        const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
+        memcpy(stage, (const char *)src + off, len);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((char *)dst + off, stage, len, cudaMemcpyHostToDevice, ctx->stage_stream[t]);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_ev[t][b], ctx->stage_stream[t]);
+      }
+      status[t] = (int)e;
+    });
+  }
+  for (auto &th : pool) th.join();
+  for (int t = 0; t < kStageThreads; ++t) {
+    if (status[t] != (int)cudaSuccess) return cuda_fail((cudaError_t)status[t], "staged host-to-device copy", __FILE__, __LINE__);
+    // the compute stream continues after the last chunk of every staging stream
+    ALS_CUDA(cudaEventRecord(ctx->stage_ev[t][0], ctx->stage_stream[t]));
+    ALS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_ev[t][0], 0));
+  }
   return ALS_OK;
 }
 
@@ -276,6 +336,13 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   ALS_CUDA(cudaMalloc(&ctx->Ginv, sizeof(float) * 64 * 64));
   ALS_CUDA(cudaMalloc(&ctx->counters, sizeof(int32_t) * 16));
   ALS_CUDA(cudaMalloc(&ctx->bad_row, sizeof(long long) * 2));
+  {
+    const long long init[2] = {LLONG_MAX, LLONG_MAX};
+    ALS_CUDA(cudaMemcpy(ctx->bad_row, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  ALS_CUDA(cudaMalloc(&ctx->status, sizeof(int32_t) * 4));
+  ALS_CUDA(cudaMemset(ctx->status, 0, sizeof(int32_t) * 4));
+  ALS_CUDA(cudaMemset(ctx->G, 0, sizeof(float) * 256 * 256));
   ALS_CUDA(cudaMalloc(&ctx->dscalars, sizeof(double) * 8));
   *out = ctx;
   return ALS_OK;
@@ -318,9 +385,18 @@ ALS_API int als_ctx_destroy(als_ctx *ctx) {
   cudaFree(ctx->deferred);
   cudaFree(ctx->counters);
   cudaFree(ctx->bad_row);
+  cudaFree(ctx->status);
   cudaFree(ctx->dscalars);
   cudaFree(ctx->scratch);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->stage_buf) {
+    cudaFreeHost(ctx->stage_buf);
+    for (int t = 0; t < 4; ++t) {
+      cudaStreamDestroy(ctx->stage_stream[t]);
+      for (int b = 0; b < 2; ++b) cudaEventDestroy(ctx->stage_ev[t][b]);
+    }
+    cudaEventDestroy(ctx->stage_ready);
+  }
   if (ctx->sched_pinned) cudaFreeHost(ctx->sched_pinned);
   cudaEventDestroy(ctx->sched_ev);
   {
@@ -467,8 +543,12 @@ ALS_API int als_csr_upload(als_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz
   }
   ALS_CUDA(cudaMemcpyAsync(c->indptr, ip, sizeof(int32_t) * (rows + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (nnz) {
-    ALS_CUDA(cudaMemcpyAsync(c->indices, indices + base, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
-    ALS_CUDA(cudaMemcpyAsync(c->data, data + base, sizeof(float) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    int hrc;
+    if ((hrc = h2d_copy(ctx, c->indices, indices + base, sizeof(int32_t) * nnz)) != ALS_OK ||
+        (hrc = h2d_copy(ctx, c->data, data + base, sizeof(float) * nnz)) != ALS_OK) {
+      als_csr_destroy(c);
+      return hrc;
+    }
   }
   int rc = build_schedule(ctx, c, ip);
   if (rc != ALS_OK) {
@@ -518,6 +598,7 @@ ALS_API int als_csr_scale(als_ctx *ctx, als_csr *csr, float alpha) {
   ALS_REQUIRE(ctx && csr, "als_csr_scale: NULL argument");
   if (csr->nnz == 0) return ALS_OK;
   ALS_CUDA(cudaSetDevice(ctx->device));
+  csr->wmax_valid = false;
   scale_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(csr->data, csr->nnz, alpha);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -567,6 +648,7 @@ ALS_API int als_csr_destroy(als_csr *csr) {
       dev_free(ctx, csr->indices);
       dev_free(ctx, csr->data);
     }
+    dev_free(ctx, csr->wmax_dev);
     dev_free(ctx, csr->work);
     dev_free(ctx, csr->finish);
     dev_free(ctx, csr->chunks);
@@ -617,7 +699,8 @@ ALS_API int als_factors_upload(als_ctx *ctx, als_factors *f, const float *host, 
   ALS_CUDA(cudaSetDevice(ctx->device));
   // ordered after any kernel already queued on the compute stream that reads/writes f
   if (f->f == f->ld) {  // no padding: one contiguous copy (a pitched copy of 256-byte rows is several times slower)
-    ALS_CUDA(cudaMemcpyAsync(f->d + row0 * f->ld, host, sizeof(float) * f->f * nrows, cudaMemcpyHostToDevice, ctx->stream));
+    int hrc = h2d_copy(ctx, f->d + row0 * f->ld, host, sizeof(float) * f->f * nrows);
+    if (hrc != ALS_OK) return hrc;
   } else {
     ALS_CUDA(cudaMemcpy2DAsync(f->d + row0 * f->ld, sizeof(float) * f->ld, host, sizeof(float) * f->f,
                                sizeof(float) * f->f, nrows, cudaMemcpyHostToDevice, ctx->stream));
@@ -776,6 +859,10 @@ static int finish_cholesky(als_ctx *ctx, const als_csr *C, als_factors *X, const
   ALS_CUDA(cudaStreamSynchronize(ctx->stream));
   if (bad_row) *bad_row = (bad == LLONG_MAX) ? -1 : (int64_t)bad;
   if (bad != LLONG_MAX) {
+    // reported here and now: nothing is left for a later als_solver_status to find
+    const long long init[2] = {LLONG_MAX, LLONG_MAX};
+    ALS_CUDA(cudaMemcpyAsync(ctx->bad_row, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    ALS_CUDA(cudaStreamSynchronize(ctx->stream));
     set_error("cholesky failed on row %lld: normal equations not positive definite. Try increasing the "
               "regularization parameter.", bad);
     return ALS_E_NOT_POSDEF;
@@ -857,6 +944,45 @@ ALS_API int als_least_squares_pregram(als_ctx *ctx, const als_csr *C, als_factor
   if (rc != ALS_OK) return rc;
   ALS_CUDA(cudaSetDevice(ctx->device));
   return finish_cholesky(ctx, C, X, Y, regularization, bad_row);
+}
+
+// The multi-GPU fit loop: the same half as als_least_squares_pregram without the host round trip for bad_row, so
+// the next half (and its collectives) are queued while this one runs; failures are collected by als_solver_status.
+ALS_API int als_least_squares_pregram_async(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
+                                            double regularization) {
+  int rc = check_half("als_least_squares_pregram_async", ctx, C, X, Y);
+  if (rc != ALS_OK) return rc;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  rc = launch_regularize(ctx, Y->f, Y->ld, (float)regularization);
+  if (rc != ALS_OK) return rc;
+  return launch_cholesky(ctx, C, X, Y);
+}
+
+ALS_API int als_solver_status(als_ctx *ctx, int64_t *bad_row, int *any_rank_failed) {
+  ALS_REQUIRE(ctx, "als_solver_status: NULL context");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  long long bad[2] = {LLONG_MAX, LLONG_MAX};
+  int32_t st = 0;
+  float flag = 0.f;
+  ALS_CUDA(cudaMemcpyAsync(bad, ctx->bad_row, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(cudaMemcpyAsync(&st, ctx->status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->gram_ld)
+    ALS_CUDA(cudaMemcpyAsync(&flag, ctx->G + ctx->gram_ld * ctx->gram_ld, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  const long long first = std::min(bad[0], bad[1]);
+  if (bad_row) *bad_row = first == LLONG_MAX ? -1 : (int64_t)first;
+  if (any_rank_failed) *any_rank_failed = (st != 0 || flag > 0.f || first != LLONG_MAX) ? 1 : 0;
+  const long long init[2] = {LLONG_MAX, LLONG_MAX};  // start a new collection period
+  ALS_CUDA(cudaMemcpyAsync(ctx->bad_row, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  ALS_CUDA(cudaMemsetAsync(ctx->status, 0, sizeof(int32_t), ctx->stream));
+  if (ctx->gram_ld) ALS_CUDA(cudaMemsetAsync(ctx->G + ctx->gram_ld * ctx->gram_ld, 0, sizeof(float), ctx->stream));
+  ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (first != LLONG_MAX) {
+    set_error("cholesky failed on row %lld: normal equations not positive definite. Try increasing the "
+              "regularization parameter.", first);
+    return ALS_E_NOT_POSDEF;
+  }
+  return ALS_OK;
 }
 
 ALS_API int als_least_squares_cg_pregram(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,

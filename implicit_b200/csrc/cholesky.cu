@@ -26,11 +26,12 @@ namespace {
 // ---- kernel ------------------------------------------------------------------------------------
 // pass 0: whole rows and chunks of giant rows;  pass 1: finish giant rows from their chunk slots.
 template <int NB>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 3)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 11)
 cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
                      float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
                      const WorkItem *__restrict__ work, int n_work, const int32_t *n_work_dev, int32_t *counter,
-                     float *slots, long long *bad_row, int pass, int dbg_arg, float *const *peers, int n_peers) {
+                     float *slots, long long *bad_row, int pass, int dbg_arg, float *const *peers, int n_peers,
+                     const unsigned *__restrict__ wmax_bits, const unsigned *__restrict__ yabsmax_bits) {
 #ifdef ALS_B200_ABLATE
   const int dbg = dbg_arg;
 #else
@@ -38,15 +39,19 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
   (void)dbg_arg;
 #endif
   using C = Cfg<NB>;
+  using C16 = Cfg16<NB>;
   constexpr int F = C::F;
   if (n_work_dev) n_work = *n_work_dev;  // a list built on the device (items deferred by the short-row kernels)
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  float *wsm = smem + warp * C::WARP_FLOATS;
+  float *wsm = smem + warp * C16::WARP_FLOATS;
   float *stages = wsm;
-  float *U = wsm + C::NSTAGE * C::STAGE_FLOATS;
+  float *U = wsm + C16::NSTAGE * C16::STAGE_FLOATS;
   float *zb = U + C::U_FLOATS;
+  // sigma: the power of two that brings the largest sqrt|w| |y| of this half just below 2^14 (fp16 operands)
+  const float sigma = pow2_scale_below_2_14(sqrtf(__uint_as_float(*wmax_bits)) * __uint_as_float(*yabsmax_bits));
+  const float sigma2 = sigma * sigma, inv_sigma2 = 1.f / sigma2;  // exact: powers of two
 
   auto fetch = [&]() -> int {
     int v = 0;
@@ -58,7 +63,7 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
     const int4 v = __ldg(reinterpret_cast<const int4 *>(work) + i);
     return WorkItem{v.x, v.y, v.z, v.w};
   };
-  auto stage_ptr = [&](int s) -> float * { return stages + (s >= C::NSTAGE ? s - C::NSTAGE : s) * C::STAGE_FLOATS; };
+  auto stage_ptr = [&](int s) -> float * { return stages + (s & 1) * C16::STAGE_FLOATS; };
   const Blk kNoBlk{-1, 0.f};
 
   // software pipeline over work items: `wi` is being processed, `wn` (+ its first index block) is
@@ -69,12 +74,11 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
   int i1 = fetch();
   WorkItem wn{0, 0, 0, -1};
   Blk b0 = kNoBlk, nb0 = kNoBlk;
-  int stage = 0;
   if (pass == 0) {
     b0 = load_block(wi, 0, indices, data, lane);
-    const int nks0 = (wi.k1 - wi.k0 + 7) >> 3;
-    issue_kstep<NB>(stage_ptr(0), b0, 0, 0 < nks0, Y, lane);
-    issue_kstep<NB>(stage_ptr(1), b0, 1, 1 < nks0, Y, lane);
+    const int nks0 = (wi.k1 - wi.k0 + 15) >> 4;
+    issue_kstep16<NB>(stage_ptr(0), b0, 0, 0 < nks0, sigma, Y, lane);
+    issue_kstep16<NB>(stage_ptr(1), b0, 1, 1 < nks0, sigma, Y, lane);
   }
   if (i1 >= 0) {
     wn = load_item(i1);
@@ -85,7 +89,9 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
   for (;;) {
     const bool whole = (wi.slot == -1), chunk = (wi.slot >= 0), finish = (wi.slot == -2);
     const int i2 = (i1 >= 0) ? fetch() : -1;  // consumed after this row's accumulation
-    // ---- initialise the accumulators: Y^T Y + lambda I for a row that will be solved, 0 for a chunk
+    // ---- initialise the accumulators: sigma^2 (Y^T Y + lambda I) for a row that will be solved here, Y^T Y +
+    //      lambda I for a finish item (its chunk partials arrive unscaled), 0 for a chunk
+    const float ginit = (pass == 0) ? sigma2 : 1.f;
 #pragma unroll
     for (int c = 0; c < C::NT8; ++c) st.bp[c] = 0.f;
 #pragma unroll
@@ -98,34 +104,34 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
         } else {
           const float2 top = __ldg(reinterpret_cast<const float2 *>(Greg + (16 * i + g) * F + 8 * j + 2 * t));
           const float2 bot = __ldg(reinterpret_cast<const float2 *>(Greg + (16 * i + g + 8) * F + 8 * j + 2 * t));
-          d[0] = top.x; d[1] = top.y; d[2] = bot.x; d[3] = bot.y;
+          d[0] = ginit * top.x; d[1] = ginit * top.y; d[2] = ginit * bot.x; d[3] = ginit * bot.y;
         }
       }
 
     WorkItem wnn{0, 0, 0, -1};
     Blk nnb0 = kNoBlk;
     if (pass == 0) {
-      const int nks = (wi.k1 - wi.k0 + 7) >> 3;
+      const int nks = (wi.k1 - wi.k0 + 15) >> 4;  // 16 nonzeros per k-step, two k-steps per 32-nonzero block
       Blk cb = b0;
-      Blk nb = (nks > 4) ? load_block(wi, 1, indices, data, lane) : kNoBlk;
+      Blk nb = (nks > 2) ? load_block(wi, 1, indices, data, lane) : kNoBlk;
       for (int ks = 0; ks < nks; ++ks) {
         cp_async_wait<1>();
         __syncwarp();
+        consume_kstep16<NB>(st, stage_ptr(ks), g, t);
+        __syncwarp();  // the stage is free again
         const int tks = ks + 2;
-        if ((tks & 3) == 0 && tks < nks) {  // the gathers move on to the next 32 nonzeros
+        if ((tks & 1) == 0 && tks < nks) {  // the gathers move on to the next 32 nonzeros
           cb = nb;
-          if (tks + 4 < nks) nb = load_block(wi, (tks >> 2) + 1, indices, data, lane);
+          if (tks + 2 < nks) nb = load_block(wi, (tks >> 1) + 1, indices, data, lane);
         }
-        issue_kstep<NB>(stage_ptr(stage + 2), cb, tks & 3, tks < nks, Y, lane);
-        consume_kstep<NB>(st, stage_ptr(stage), g, t);
-        if (++stage == C::NSTAGE) stage = 0;
+        issue_kstep16<NB>(stage_ptr(ks), cb, tks & 1, tks < nks, sigma, Y, lane);
       }
-      __syncwarp();
-      // the first two k-steps of the next item land while this row is factored
+      // the first two k-steps of the next item land while this row is factored (both stages are free: the two
+      // groups committed last were empty)
       if (i1 >= 0) {
-        const int nks1 = (wn.k1 - wn.k0 + 7) >> 3;
-        issue_kstep<NB>(stage_ptr(stage), nb0, 0, 0 < nks1, Y, lane);
-        issue_kstep<NB>(stage_ptr(stage + 1), nb0, 1, 1 < nks1, Y, lane);
+        const int nks1 = (wn.k1 - wn.k0 + 15) >> 4;
+        issue_kstep16<NB>(stage_ptr(0), nb0, 0, 0 < nks1, sigma, Y, lane);
+        issue_kstep16<NB>(stage_ptr(1), nb0, 1, 1 < nks1, sigma, Y, lane);
       }
       if (i2 >= 0) {
         wnn = load_item(i2);
@@ -146,11 +152,11 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
     }
 
     if (chunk) {
-      float *sl = slots + (int64_t)wi.slot * C::SLOT_FLOATS;
+      float *sl = slots + (int64_t)wi.slot * C::SLOT_FLOATS;  // partials leave the scaled domain
 #pragma unroll
       for (int e = 0; e < C::NTILES; ++e)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) sl[(e * 4 + v) * 32 + lane] = st.acc[e][v];
+        for (int v = 0; v < 4; ++v) sl[(e * 4 + v) * 32 + lane] = st.acc[e][v] * inv_sigma2;
 #pragma unroll
       for (int c = 0; c < C::NT8; ++c) sl[(C::NTILES * 4 + c) * 32 + lane] = st.bp[c];
     } else {
@@ -164,6 +170,10 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
       } else if (whole || finish) {
         bool ok = true;
         if (!(dbg & 8)) {
+          if (pass == 0) {  // (sigma^2 A) x = sigma^2 b
+#pragma unroll
+            for (int c = 0; c < C::NT8; ++c) st.bp[c] *= sigma2;
+          }
           float xx[(F + 31) / 32];
           factor_solve<NB>(st, U, zb, lane, ok, dbg, xx);
           if (ok) store_solution<F>(xx, xout, lane, peers, n_peers, (row_offset + wi.row) * F);
@@ -182,9 +192,43 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
   cp_async_wait<0>();
 }
 
+// max over [begin, end) of | |c| - 1 | (bits; NaN / inf left out) -- the weight range of a CSR, cached in the handle
+__global__ void __launch_bounds__(256) csr_wmax_kernel(const int32_t *__restrict__ indptr, int64_t rows,
+                                                       const float *__restrict__ data, unsigned *out) {
+  const int64_t begin = indptr[0], end = indptr[rows];
+  unsigned m = 0;
+  for (int64_t e = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < end; e += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned b = __float_as_uint(fabsf(fabsf(__ldg(data + e)) - 1.f));
+    if (b < 0x7f800000u) m = max(m, b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// max |y| over a factor matrix (bits; NaN / inf left out)
+__global__ void __launch_bounds__(256) factors_absmax_kernel(const float4 *__restrict__ y, int64_t n4, unsigned *out) {
+  unsigned m = 0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(y + e);
+    const unsigned b[4] = {__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu,
+                           __float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (b[j] < 0x7f800000u) m = max(m, b[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 __global__ void init_solver_scalars(int32_t *counters, long long *bad_row) {
   if (threadIdx.x < 16) counters[threadIdx.x] = 0;
-  if (threadIdx.x == 0) bad_row[0] = LLONG_MAX;
+  if (threadIdx.x == 0) {
+    // [1] keeps the first bad row of every half since the last als_solver_status (the asynchronous multi-GPU fit)
+    if (bad_row[0] < bad_row[1]) bad_row[1] = bad_row[0];
+    bad_row[0] = LLONG_MAX;
+  }
 }
 
 // Timing ablations (tools/ablate.py) exist only in builds with -DALS_B200_ABLATE: ALS_B200_DEBUG bit0 skips the back
@@ -207,7 +251,7 @@ template <int NB>
 int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_factors *Y) {
   using C = Cfg<NB>;
   const int dbg = debug_flags();
-  const int smem = C::WARP_FLOATS * kWarpsPerCta * (int)sizeof(float);
+  const int smem = Cfg16<NB>::WARP_FLOATS * kWarpsPerCta * (int)sizeof(float);
   auto kern = cholesky_half_kernel<NB>;
   ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int ctas_per_sm = 0;
@@ -225,6 +269,25 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
   init_solver_scalars<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->bad_row);
   ALS_CUDA(cudaGetLastError());
   ctx->launches++;
+  // the range of the fp16-split operands: max |y| of this half (one pass over Y) and max | |c| - 1 | of the CSR
+  // (one pass over its values, cached in the handle until als_csr_scale changes them)
+  unsigned *yabsmax = reinterpret_cast<unsigned *>(ctx->counters + kCtrYAbsMax);
+  factors_absmax_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(Y->d),
+                                                                     std::max<int64_t>(Y->rows, 0) * (Y->ld / 4), yabsmax);
+  ALS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  als_csr *Cmut = const_cast<als_csr *>(Cm);
+  if (!Cmut->wmax_dev) {
+    int arc = dev_alloc(ctx, (void **)&Cmut->wmax_dev, sizeof(unsigned));  // stream-ordered pool: no cudaMalloc per fit
+    if (arc != ALS_OK) return arc;
+  }
+  if (!Cmut->wmax_valid) {
+    ALS_CUDA(cudaMemsetAsync(Cmut->wmax_dev, 0, sizeof(unsigned), ctx->stream));
+    csr_wmax_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(Cm->indptr, Cm->rows, Cm->data, Cmut->wmax_dev);
+    ALS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    Cmut->wmax_valid = true;
+  }
   // Items of at most `short_max` nonzeros (a suffix of the length-sorted work list) go through the n x n
   // push-through system of cholesky_short.cu when there are enough of them to pay for whitening Y.
   int short_max = std::min(ctx->knobs.short_max, 16 * (NB - 1));
@@ -256,7 +319,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
       const int grid = (int)std::min<int64_t>(ceil_div(n_main, kWarpsPerCta), max_grid);
       kern<<<grid, 32 * kWarpsPerCta, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
                                                             Cm->work, (int)n_main, nullptr, ctx->counters + kCtrMain,
-                                                            slots, ctx->bad_row, 0, dbg, X->peers_dev, X->n_peers);
+                                                            slots, ctx->bad_row, 0, dbg, X->peers_dev, X->n_peers, Cm->wmax_dev, yabsmax);
       ALS_CUDA(cudaGetLastError());
       ctx->launches++;
     }
@@ -268,7 +331,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
       kern<<<grid, 32 * kWarpsPerCta, smem, side>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
                                                      ctx->deferred, 0, ctx->counters + kCtrDeferredCount,
                                                      ctx->counters + kCtrDeferredWork, slots, ctx->bad_row, 0, dbg,
-                                                     X->peers_dev, X->n_peers);
+                                                     X->peers_dev, X->n_peers, Cm->wmax_dev, yabsmax);
       ALS_CUDA(cudaGetLastError());
       ctx->launches++;
       if (overlap) {
@@ -284,7 +347,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
     kern<<<grid, 32 * kWarpsPerCta, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
                                                           Cm->finish, (int)Cm->n_finish, nullptr,
                                                           ctx->counters + kCtrFinish, slots,
-                                                          ctx->bad_row, 1, dbg, X->peers_dev, X->n_peers);
+                                                          ctx->bad_row, 1, dbg, X->peers_dev, X->n_peers, Cm->wmax_dev, yabsmax);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
   }

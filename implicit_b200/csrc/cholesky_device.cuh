@@ -5,6 +5,8 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "common.h"
 
 namespace als {
@@ -78,7 +80,7 @@ struct Cfg {
   static constexpr int SLOT_FLOATS = 32 * (NTILES * 4 + NT8);
 };
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 1;  // warps share nothing: one-warp CTAs let shared memory (19.5 KB each), not CTA granularity, set the occupancy
 
 template <int NB>
 struct RowState {
@@ -166,6 +168,118 @@ __device__ __forceinline__ void consume_kstep(RowState<NB> &st, const float *sta
         float(&d)[4] = st.acc[C::tidx(i, j)];
         if (term == 1) mma_tf32(d, a0, a1, a2, a3, vl0[j], vl1[j]);  // hi * lo
         else mma_tf32(d, a0, a1, a2, a3, vh0[j], vh1[j]);            // lo * hi, then hi * hi
+      }
+    }
+  }
+}
+
+// ---- fp16-split accumulation: 16 nonzeros per k-step on mma.sync.m16n8k16 ---------------------------------
+// v = sigma sqrt|w| y is split into an fp16 pair hi + lo (both rounded to nearest: 22 bits of every value that is
+// not tiny against the largest one), with sigma a power of two chosen per half-iteration from max|w| and max|y| so
+// that the largest product stays below 2^14.  A_u is then accumulated as  sigma^2 A_u  (the solve is invariant).
+// Three HMMAs per tile and 16 nonzeros instead of three per 8: half the tensor instructions of the 3xTF32 path.
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void split_f16_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// biased exponent field of the power of two that scales a positive maximum p to just below 2^14 (see topk_tc.cu)
+__device__ __forceinline__ float pow2_scale_below_2_14(float p) {
+  const unsigned b = __float_as_uint(p);
+  const int E = (int)(b >> 23) & 0xff;
+  int se = (b & 0x7fffffffu) ? 267 - E : 127;
+  se = se < 1 ? 1 : se > 253 ? 253 : se;
+  return __uint_as_float((unsigned)se << 23);
+}
+
+template <int NB>
+struct Cfg16 {
+  using C = Cfg<NB>;
+  static constexpr int F = C::F;
+  static constexpr int LDS = F + 4;          // staged-row stride: rows 2t, 2t+1, 2t+8, 2t+9 hit distinct banks
+  static constexpr int NSTAGE = 2;
+  static constexpr int STAGE_FLOATS = 16 * LDS + 32;  // 16 rows + sw[16] + cpos[16]
+  static constexpr int WARP_FLOATS = NSTAGE * STAGE_FLOATS + C::U_FLOATS + F /* z */;
+};
+
+// gather: k-step s2 (0..1) of block `blk` (32 nonzeros in registers, one per lane) -> stage
+template <int NB>
+__device__ __forceinline__ void issue_kstep16(float *stage, const Blk &blk, int s2, bool active, float sigma,
+                                              const float *__restrict__ Y, int lane) {
+  using C = Cfg16<NB>;
+  if (active) {  // warp uniform
+    const int src = 16 * s2 + (lane & 15);
+    const float c = __shfl_sync(0xffffffffu, blk.c, src);
+    const int myidx = __shfl_sync(0xffffffffu, blk.idx, src);
+    if (lane < 16) {
+      // A += w y y^T with w = |c| - 1 = sign(w) (sqrt|w| y)(sqrt|w| y)^T; b += c y for c > 0   (_als.pyx:115-124)
+      const float w = (myidx >= 0) ? fabsf(c) - 1.f : 0.f;
+      stage[16 * C::LDS + lane] = copysignf(sigma * __fsqrt_rn(fabsf(w)), w);
+      stage[16 * C::LDS + 16 + lane] = (myidx >= 0 && c > 0.f) ? c : 0.f;
+    }
+    const int first = __shfl_sync(0xffffffffu, blk.idx, 16 * s2);  // the first row of an active k-step exists
+    constexpr int CH = C::F / 4;  // 16-byte chunks per factor row
+#pragma unroll
+    for (int q = 0; q < 2 * NB; ++q) {
+      const int id = q * 32 + lane;
+      const int row = id / CH, ch = id % CH;
+      int ridx = __shfl_sync(0xffffffffu, blk.idx, 16 * s2 + row);
+      if (ridx < 0) ridx = first;  // padding rows carry sw = cp = 0
+      cp_async16(stage + row * C::LDS + ch * 4, Y + (int64_t)ridx * C::F + ch * 4);
+    }
+  }
+  cp_async_commit();
+}
+
+// accumulate one k-step (16 nonzeros)
+template <int NB>
+__device__ __forceinline__ void consume_kstep16(RowState<NB> &st, const float *stage, int g, int t) {
+  using C = Cfg<NB>;
+  constexpr int LDS = Cfg16<NB>::LDS;
+  const float2 s0 = *reinterpret_cast<const float2 *>(stage + 16 * LDS + 2 * t);       // nonzeros 2t, 2t+1
+  const float2 s1 = *reinterpret_cast<const float2 *>(stage + 16 * LDS + 2 * t + 8);   // nonzeros 2t+8, 2t+9
+  const float2 c0 = *reinterpret_cast<const float2 *>(stage + 16 * LDS + 16 + 2 * t);
+  const float2 c1 = *reinterpret_cast<const float2 *>(stage + 16 * LDS + 16 + 2 * t + 8);
+  const float a00 = fabsf(s0.x), a01 = fabsf(s0.y), a10 = fabsf(s1.x), a11 = fabsf(s1.y);
+  // sign of w on the A side: flip the halves of the packed pairs
+  const uint32_t m0 = ((__float_as_uint(s0.x) >> 16) & 0x8000u) | (__float_as_uint(s0.y) & kSignBit);
+  const uint32_t m1 = ((__float_as_uint(s1.x) >> 16) & 0x8000u) | (__float_as_uint(s1.y) & kSignBit);
+  uint32_t h0[C::NT8], l0[C::NT8], h1[C::NT8], l1[C::NT8];
+  const float *r00 = stage + (2 * t) * LDS + g, *r01 = r00 + LDS, *r10 = r00 + 8 * LDS, *r11 = r10 + LDS;
+#pragma unroll
+  for (int c = 0; c < C::NT8; ++c) {
+    const float y00 = r00[8 * c], y01 = r01[8 * c], y10 = r10[8 * c], y11 = r11[8 * c];
+    st.bp[c] = fmaf(c0.x, y00, st.bp[c]);
+    st.bp[c] = fmaf(c0.y, y01, st.bp[c]);
+    st.bp[c] = fmaf(c1.x, y10, st.bp[c]);
+    st.bp[c] = fmaf(c1.y, y11, st.bp[c]);
+    split_f16_pair(a00 * y00, a01 * y01, h0[c], l0[c]);  // one split serves both mma operands
+    split_f16_pair(a10 * y10, a11 * y11, h1[c], l1[c]);
+  }
+#pragma unroll
+  for (int term = 0; term < 3; ++term) {  // lo * hi, hi * lo, hi * hi: term major (see consume_kstep)
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const uint32_t a0 = (term == 0 ? l0[2 * i] : h0[2 * i]) ^ m0;
+      const uint32_t a1 = (term == 0 ? l0[2 * i + 1] : h0[2 * i + 1]) ^ m0;
+      const uint32_t a2 = (term == 0 ? l1[2 * i] : h1[2 * i]) ^ m1;
+      const uint32_t a3 = (term == 0 ? l1[2 * i + 1] : h1[2 * i + 1]) ^ m1;
+#pragma unroll
+      for (int j = 2 * i; j < C::NT8; ++j) {
+        float(&d)[4] = st.acc[C::tidx(i, j)];
+        if (term == 1) mma_f16(d, a0, a1, a2, a3, l0[j], l1[j]);
+        else mma_f16(d, a0, a1, a2, a3, h0[j], h1[j]);
       }
     }
   }

@@ -228,14 +228,6 @@ int run_whiten_rows(als_ctx *ctx, const als_factors *Y, cudaStream_t stream) {
 // ---- the batched short-row solver ----------------------------------------------------------------
 constexpr int kBatchWarps = 4;
 
-__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                        uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
 // lanes per system for a system of NS unknowns: the register footprint of the distributed upper triangle is
 // G Q (Q + 1) / 2 with Q = NS / G columns per lane -> 36 / 72 / 84 / 80 / 120 / 96 registers
 template <int NS> struct BatchShape;
@@ -542,20 +534,33 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
       float x0 = 0.f, x1 = 0.f;  // no observations: the reference zeroes the row (_als.pyx:98-100)
       const int *ix = idxs + b * NS;
       const float *tv = zs + b * NS;
-      for (int i0 = 0; i0 < n; i0 += 8) {  // the padding up to a multiple of 8 has t = 0 and a valid index
-        const int4 ia = *reinterpret_cast<const int4 *>(ix + i0), ib = *reinterpret_cast<const int4 *>(ix + i0 + 4);
-        const float4 ta = *reinterpret_cast<const float4 *>(tv + i0), tb = *reinterpret_cast<const float4 *>(tv + i0 + 4);
-        const int id[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-        const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-        float2 zz[8];
+      // all NS slots are gathered, 16 loads in flight at a time: the padding has t = 0 and repeats a valid index, and
+      // unconditional loads let the whole chunk be issued before the first use (one latency exposure per 16 rows of Z)
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          zz[u] = owns ? __ldcg(reinterpret_cast<const float2 *>(Z + (int64_t)id[u] * F) + lane) : make_float2(0.f, 0.f);
+      for (int i0 = 0; i0 < NS; i0 += 16) {
+        constexpr int kMaxChunk = 16;
+        const int cn = NS - i0 < kMaxChunk ? NS - i0 : kMaxChunk;  // 16 or 8 (compile time after unrolling)
+        if (i0 >= n) break;                                        // warp uniform
+        int id[kMaxChunk];
+        float tt[kMaxChunk];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          x0 = fmaf(tt[u], zz[u].x, x0);
-          x1 = fmaf(tt[u], zz[u].y, x1);
-        }
+        for (int u = 0; u < kMaxChunk; u += 4)
+          if (u < cn) {
+            const int4 iv = *reinterpret_cast<const int4 *>(ix + i0 + u);
+            const float4 tv4 = *reinterpret_cast<const float4 *>(tv + i0 + u);
+            id[u] = iv.x; id[u + 1] = iv.y; id[u + 2] = iv.z; id[u + 3] = iv.w;
+            tt[u] = tv4.x; tt[u + 1] = tv4.y; tt[u + 2] = tv4.z; tt[u + 3] = tv4.w;
+          }
+        float2 zz[kMaxChunk];
+#pragma unroll
+        for (int u = 0; u < kMaxChunk; ++u)
+          if (u < cn) zz[u] = owns ? __ldcg(reinterpret_cast<const float2 *>(Z + (int64_t)id[u] * F) + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kMaxChunk; ++u)
+          if (u < cn) {
+            x0 = fmaf(tt[u], zz[u].x, x0);
+            x1 = fmaf(tt[u], zz[u].y, x1);
+          }
       }
       if (owns) {
         *reinterpret_cast<float2 *>(X + xoff + 2 * lane) = make_float2(x0, x1);

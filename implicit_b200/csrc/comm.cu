@@ -77,7 +77,8 @@ int nccl_fail(ncclResult_t r, const char *what) {
 
 int comm_allreduce_gramian(als_ctx *ctx, int n_floats) {
   if (ctx->world == 1 || !ctx->comm) return ALS_OK;
-  ALS_NCCL(g_nccl.AllReduce(ctx->G, ctx->G, (size_t)n_floats, ncclFloat, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  // + 1: the failure flag written by gramian_reduce_kernel (see als_solver_status)
+  ALS_NCCL(g_nccl.AllReduce(ctx->G, ctx->G, (size_t)n_floats + 1, ncclFloat, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
   return ALS_OK;
 }
 

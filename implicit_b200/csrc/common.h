@@ -82,7 +82,9 @@ struct als_ctx {
   int64_t gram_partials_cap = 0;
   // per-launch scalars, see the kCtr* slots below (16 ints, zeroed before every half)
   int32_t *counters = nullptr;
-  long long *bad_row = nullptr;
+  long long *bad_row = nullptr;   // [0] first non-PD row of the current half, [1] of the halves since als_solver_status
+  int32_t *status = nullptr;      // [0] sticky: some rank reported a failed half (rides on the Gramian all-reduce)
+  int gram_ld = 0;                // ld of the last regularised Gramian: G[ld * ld] is the failure flag slot
   double *dscalars = nullptr;  // loss accumulators (8 doubles)
   // short-row path of the Cholesky half (cholesky_short.cu): P = R^-1 with G + lambda I = R^T R, the whitened
   // factors W = Y P, and the list of short items handed back to the full-size kernel
@@ -101,6 +103,11 @@ struct als_ctx {
   // pinned host staging
   void *pinned = nullptr;
   int64_t pinned_bytes = 0;
+  // staged uploads of pageable host memory (api.cu h2d_copy): 4 threads x 2 page-locked 4 MB buffers, own streams
+  void *stage_buf = nullptr;
+  cudaStream_t stage_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  cudaEvent_t stage_ready = nullptr;
   // a transposed CSR whose schedule has not been built yet (csr.cu): its indptr lands here, asynchronously
   struct als_csr *sched_owner = nullptr;
   int32_t *sched_pinned = nullptr;
@@ -141,6 +148,8 @@ struct als_csr {
   // work is sorted by length, so the items of at most 48 / 40 / ... / 8 / 0 nonzeros are suffixes: first index of each
   int64_t le_begin[7] = {0, 0, 0, 0, 0, 0, 0};
   int64_t max_row_nnz = 0;     // longest row (known once the schedule is built)
+  unsigned *wmax_dev = nullptr;  // device scalar: bits of max | |c| - 1 | over the values (cholesky.cu), computed lazily
+  bool wmax_valid = false;
   bool sched_pending = false;  // transposed on the device: the schedule is built at first use (ensure_schedule)
   als::WorkItem *finish = nullptr;  // finish pass: one per giant row (row, first slot, #slots)
   int64_t n_finish = 0;
@@ -162,7 +171,7 @@ enum { kProfGramian = 0, kProfCholesky = 1, kProfCholFinish = 2, kProfCg = 3, kP
 
 // slots of als_ctx::counters
 enum {
-  kCtrMain = 0, kCtrFinish = 1, kCtrDeferredCount = 2, kCtrDeferredWork = 3, kCtrWhitenOk = 4, kCtrHasNan = 5,
+  kCtrMain = 0, kCtrFinish = 1, kCtrDeferredCount = 2, kCtrDeferredWork = 3, kCtrWhitenOk = 4, kCtrHasNan = 5, kCtrYAbsMax = 6,
   kCtrShort = 8 /* +0..5: one per short-row size class */
 };
 // size classes of the short-row path: als_csr::le_begin[i] is the first work item of at most kShortThresholds[i] nonzeros
@@ -195,6 +204,7 @@ int short_rows_prepare(als_ctx *ctx, const als_factors *Y, cudaStream_t stream);
 int launch_dense_whiten(als_ctx *ctx, const als_factors *Y, cudaStream_t stream);
 // G = Y^T Y on the tcgen05 tensor cores (dense.cu; 64 padded factors, Y of at least one row) -> ctx->G
 int launch_gramian_tc(als_ctx *ctx, const als_factors *Y);
+int launch_gramian_reduce(als_ctx *ctx, int nparts, int n);  // ctx->gram_partials (nparts x n) -> ctx->G, fixed-order fp64 sums
 int short_rows_launch(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t begin, int max_len,
                       cudaStream_t stream);
 int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int cg_steps);

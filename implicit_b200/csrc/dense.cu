@@ -314,7 +314,8 @@ constexpr int kGramT = 4 * kBoxBytes;             // [128 operand rows][128 K] a
 constexpr int kGramOffT = 2 * kGramRaw;           // after the 2 raw stages
 constexpr int kGramOffBar = kGramOffT + 2 * kGramT;
 constexpr int kGramSmem = kGramOffBar + 128 + 1024;
-enum { kGFull0 = 0, kGFull1, kGRawFree0, kGRawFree1, kGReady0, kGReady1, kGMma0, kGMma1, kGAllDone, kGNumBars };
+enum { kGFull0 = 0, kGFull1, kGRawFree0, kGRawFree1, kGReady0, kGReady1, kGMma0, kGMma1, kGAccFull0, kGAccFull1, kGAccFree0,
+       kGAccFree1, kGNumBars };
 
 // kind::tf32, fp32 accumulate, A and B K-major, M = 64, N = 128
 constexpr uint32_t kIdescGram = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
@@ -330,6 +331,9 @@ __device__ __forceinline__ void umma_tf32_idesc(uint32_t tmem_d, uint64_t adesc,
       : "memory");
 }
 
+// The tensor core adds into its fp32 accumulator with truncation (measured: a 250-step chain over all-positive
+// data is biased by 1.2e-5), so a chain is kept to 8 MMAs = 64 rows of Y: two TMEM accumulators alternate, and the
+// worker warps drain each finished chain into fp32 registers with ordinary round-to-nearest additions.
 __global__ void __launch_bounds__(kDenseThreads, 1)
 gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float *__restrict__ partials) {
   extern __shared__ unsigned char dense_smem_raw[];
@@ -341,6 +345,7 @@ gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float 
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gbase + kGramOffBar + 8 * kGNumBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_chains = 2 * my_tiles;
 
   if (threadIdx.x == 0) {
     mbar_init(bar(kGFull0), 1);
@@ -351,12 +356,15 @@ gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float 
     mbar_init(bar(kGReady1), 128);
     mbar_init(bar(kGMma0), 1);
     mbar_init(bar(kGMma1), 1);
-    mbar_init(bar(kGAllDone), 1);
+    mbar_init(bar(kGAccFull0), 1);
+    mbar_init(bar(kGAccFull1), 1);
+    mbar_init(bar(kGAccFree0), 128);
+    mbar_init(bar(kGAccFree1), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
-                 "r"(128)
+                 "r"(256)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -378,26 +386,50 @@ gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t acc = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
         mbar_wait(bar(kGReady0 + s), (uint32_t)((t >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t T = base + kGramOffT + s * kGramT;
 #pragma unroll
-        for (int ks = 0; ks < kTileM / 8; ++ks) {  // 8 rows of Y (the K extent of a tf32 MMA) per instruction
-          const uint64_t d = umma_desc_k_sw128(T + (uint32_t)((ks >> 2) * kBoxBytes + (ks & 3) * 32));
-          umma_tf32_idesc(tmem_base, d, d, kIdescGram, acc);
-          acc = 1;
+        for (int h = 0; h < 2; ++h) {  // a chain = 8 MMAs = 64 rows of Y into accumulator (2t + h) & 1
+          const int c = 2 * t + h, a = c & 1;
+          if (c >= 2) mbar_wait(bar(kGAccFree0 + a), (uint32_t)(((c >> 1) - 1) & 1));  // chain c - 2 has been drained
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const int ks = 8 * h + k8;  // 8 rows of Y (the K extent of a tf32 MMA) per instruction
+            const uint64_t d = umma_desc_k_sw128(T + (uint32_t)((ks >> 2) * kBoxBytes + (ks & 3) * 32));
+            umma_tf32_idesc(tmem_base + (uint32_t)(a * 128), d, d, kIdescGram, k8 ? 1u : 0u);
+          }
+          umma_commit(bar(kGAccFull0 + a));
         }
-        umma_commit(bar(kGMma0 + s));
+        umma_commit(bar(kGMma0 + s));  // the operand tile may be overwritten
       }
-      umma_commit(bar(kGAllDone));
     }
   } else {
-    // ===== workers: split + transpose the landed tile into the operand tile =====
+    // ===== workers: split + transpose the landed tile into the operand tile; drain finished chains =====
     const int w4 = warp & 3;               // K-chunk of the operand tile = rows 32 w4 .. 32 w4 + 31 of the Y tile
     const int r = 32 * w4 + lane;          // this lane's row of the Y tile
+    // lanes 0..15 of warp quarter w4 hold row 16 w4 + lane of the 64 x 128 accumulator (M = 64 uses half of every
+    // 32-lane quarter): columns 0..63 = hi^T hi, 64..127 = hi^T lo
+    float racc[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) racc[j] = 0.f;
+    auto drain = [&](int c) {
+      const int a = c & 1;
+      mbar_wait(bar(kGAccFull0 + a), (uint32_t)((c >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * w4) << 16) + (uint32_t)(a * 128 + 32 * q), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) racc[32 * q + j] += __uint_as_float(v[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar(kGAccFree0 + a));
+    };
     for (int t = 0; t < my_tiles; ++t) {
       const int s = t & 1;
       mbar_wait(bar(kGFull0 + s), (uint32_t)((t >> 1) & 1));
@@ -422,43 +454,35 @@ gramian_tc_kernel(const __grid_constant__ CUtensorMap map_y, int n_tiles, float 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar(kGReady0 + s));
       mbar_arrive(bar(kGRawFree0 + s));
-    }
-    // the 64 x 128 accumulator: rows 16 q .. 16 q + 15 live in lanes 32 q .. 32 q + 15 (M = 64 uses half of every
-    // 32-lane quarter), so lanes 0..15 of each worker warp hold one row each
-    mbar_wait(bar(kGAllDone), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float *out = partials + ((size_t)blockIdx.x * 64 + 16 * w4 + lane) * 128;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(32 * w4) << 16) + (uint32_t)(32 * c), v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (lane < 16) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4 *>(out + 32 * c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      if (t >= 1) {  // the two chains of the previous tile (its MMAs ran while this tile was transposed)
+        drain(2 * t - 2);
+        drain(2 * t - 1);
       }
+    }
+    if (my_tiles > 0) {
+      drain(n_chains - 2);
+      drain(n_chains - 1);
+    }
+    // partial of this CTA, symmetrised: P = S1 + S2 + S2^T (S2^T through shared memory: raw stage 0 is free now)
+    float *s2 = reinterpret_cast<float *>(gbase);  // [64][65]
+    const int row = 16 * w4 + lane;
+    if (lane < 16) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) s2[row * 65 + j] = racc[64 + j];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (lane < 16) {
+      float *out = partials + ((size_t)blockIdx.x * 64 + row) * 64;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) out[j] = racc[j] + (racc[64 + j] + s2[j * 65 + row]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
-}
-
-// G[i][j] = sum over CTAs of S1[i][j] + S2[i][j] + S2[j][i], in fp64, CTAs in index order
-__global__ void __launch_bounds__(256) gramian_tc_reduce_kernel(const float *__restrict__ partials, int nparts, float *__restrict__ G) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 64 * 64) return;
-  const int i = e >> 6, j = e & 63;
-  double s = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    const float *P = partials + (size_t)p * 64 * 128;
-    s += (double)P[i * 128 + j] + ((double)P[i * 128 + 64 + j] + (double)P[j * 128 + 64 + i]);
-  }
-  G[e] = (float)s;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -535,7 +559,7 @@ int launch_gramian_tc(als_ctx *ctx, const als_factors *Y) {
   const int64_t rows = std::max<int64_t>(Y->rows, 1);
   const int n_tiles = (int)ceil_div(rows, kTileM);
   const int grid = std::min(n_tiles, ctx->sm_count);
-  const int64_t need = (int64_t)grid * 64 * 128;
+  const int64_t need = (int64_t)grid * 64 * 64;
   if (need > ctx->gram_partials_cap) {
     if (ctx->gram_partials) {
       ALS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -552,10 +576,8 @@ int launch_gramian_tc(als_ctx *ctx, const als_factors *Y) {
   ALS_CUDA(cudaFuncSetAttribute(gramian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
   gramian_tc_kernel<<<grid, kDenseThreads, kGramSmem, ctx->stream>>>(my, n_tiles, ctx->gram_partials);
   ALS_CUDA(cudaGetLastError());
-  gramian_tc_reduce_kernel<<<16, 256, 0, ctx->stream>>>(ctx->gram_partials, grid, ctx->G);
-  ALS_CUDA(cudaGetLastError());
-  ctx->launches += 2;
-  return ALS_OK;
+  ctx->launches += 1;
+  return launch_gramian_reduce(ctx, grid, 64 * 64);  // partials summed in fp64 in a fixed order (gramian.cu)
 }
 
 }  // namespace als

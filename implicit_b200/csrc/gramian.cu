@@ -8,6 +8,8 @@
 //             the upper-triangular 16x8 tiles with mma.sync 3xTF32 (the accumulation step of cholesky.cu with unit
 //             weights: fp32-faithful), the 8 warps of a CTA are summed in a fixed tree;
 //   f <= 128: gramian_partial_kernel -- fp32 FMA register tiles (the CG configurations).
+#include <limits.h>
+
 #include "cholesky_device.cuh"
 
 namespace als {
@@ -190,8 +192,11 @@ __global__ void __launch_bounds__(256) gramian_partial_kernel(const float *__res
 
 // 32 consecutive elements x 8 groups of partials per block: group pg sums partials pg, pg + 8, ... in fp64, the 8
 // group sums are added in a fixed order -> deterministic, and the loads of a warp are contiguous.
+// (Multi-GPU) element n of G carries "a row of this rank's last solve was not positive definite": the all-reduce of
+// the Gramian then tells every rank that some rank failed, without any extra collective or host round trip.
 __global__ void __launch_bounds__(256) gramian_reduce_kernel(const float *__restrict__ partials, int nparts, int n,
-                                                             float *__restrict__ G) {
+                                                             float *__restrict__ G, const long long *__restrict__ bad_row) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) G[n] = (bad_row[0] != LLONG_MAX || bad_row[1] != LLONG_MAX) ? 1.f : 0.f;
   __shared__ double part[8][33];
   const int el = threadIdx.x & 31, pg = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + el;
@@ -211,8 +216,10 @@ __global__ void __launch_bounds__(256) gramian_reduce_kernel(const float *__rest
 // Greg = G + lambda I on the real dimensions, identity on the zero-padded ones (so that padded
 // unknowns solve to exactly 0 even with lambda == 0).  Mirrors `YtY + regularization * np.eye(f)`
 // (implicit/cpu/_als.pyx:85, :164): an fp32 add of fp32(lambda).
-__global__ void regularize_kernel(const float *__restrict__ G, float *__restrict__ Greg, int f, int ld, float lambda) {
+__global__ void regularize_kernel(const float *__restrict__ G, float *__restrict__ Greg, int f, int ld, float lambda,
+                                  int32_t *__restrict__ status) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0 && G[ld * ld] > 0.f) status[0] = 1;  // the flag that rode along with the all-reduced Gramian (sticky)
   if (e >= ld * ld) return;
   const int i = e / ld, j = e % ld;
   float v = G[e];
@@ -280,14 +287,22 @@ int launch_gramian(als_ctx *ctx, const als_factors *Y) {
   }
   if (rc != ALS_OK) return rc;
   ALS_CUDA(cudaGetLastError());
-  gramian_reduce_kernel<<<(F * F + 31) / 32, 256, 0, ctx->stream>>>(ctx->gram_partials, grid, F * F, ctx->G);
+  gramian_reduce_kernel<<<(F * F + 31) / 32, 256, 0, ctx->stream>>>(ctx->gram_partials, grid, F * F, ctx->G, ctx->bad_row);
   ALS_CUDA(cudaGetLastError());
   ctx->launches += 2;
   return ALS_OK;
 }
 
+int launch_gramian_reduce(als_ctx *ctx, int nparts, int n) {
+  gramian_reduce_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(ctx->gram_partials, nparts, n, ctx->G, ctx->bad_row);
+  ALS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return ALS_OK;
+}
+
 int launch_regularize(als_ctx *ctx, int f, int ld, float lambda) {
-  regularize_kernel<<<(ld * ld + 255) / 256, 256, 0, ctx->stream>>>(ctx->G, ctx->Greg, f, ld, lambda);
+  regularize_kernel<<<(ld * ld + 255) / 256, 256, 0, ctx->stream>>>(ctx->G, ctx->Greg, f, ld, lambda, ctx->status);
+  ctx->gram_ld = ld;
   ALS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return ALS_OK;

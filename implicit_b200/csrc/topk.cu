@@ -17,6 +17,9 @@
 #include <limits.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cub/device/device_segmented_radix_sort.cuh>
+
 #include "common.h"
 
 namespace als {
@@ -361,6 +364,111 @@ int run_topk(als_ctx *ctx, const TopkArgs &a) {
   return ALS_OK;
 }
 
+// ---- very large k (the k-lists no longer fit in shared memory): scores to HBM, one stable segmented sort --------
+// rank_items / recommend with N in the thousands up to "all items" (the reference's select.h takes any k).  One CTA per
+// query row writes the filtered score row (fp32 FMA dot products), cub sorts every row descending by score (stable:
+// equal scores keep ascending item order, so the boundary of the first k prefers the smaller column like select.h:23),
+// and the host reverses each run of equal scores (select.h:33 emits larger columns first).
+__global__ void __launch_bounds__(256) score_rows_kernel(const float *__restrict__ items, int n_items, int ld,
+                                                         const float *__restrict__ queries, const int32_t *__restrict__ query_rows,
+                                                         int q0, const float *__restrict__ norms, const uint8_t *__restrict__ mask,
+                                                         const int32_t *__restrict__ liked_indptr,
+                                                         const int32_t *__restrict__ liked_indices, float *__restrict__ S,
+                                                         int32_t *__restrict__ ids) {
+  extern __shared__ float qrow[];
+  const int q = q0 + blockIdx.x;
+  const int64_t src = query_rows ? query_rows[q] : q;
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) qrow[j] = queries[src * ld + j];
+  __syncthreads();
+  float *out = S + (int64_t)blockIdx.x * n_items;
+  int32_t *oid = ids + (int64_t)blockIdx.x * n_items;
+  for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+    const float4 *it = reinterpret_cast<const float4 *>(items + (int64_t)i * ld);
+    float acc = 0.f;
+    for (int j = 0; j < ld / 4; ++j) {
+      const float4 v = __ldg(it + j);
+      acc = fmaf(v.x, qrow[4 * j], fmaf(v.y, qrow[4 * j + 1], fmaf(v.z, qrow[4 * j + 2], fmaf(v.w, qrow[4 * j + 3], acc))));
+    }
+    if (norms) acc /= norms[i];                 // topk.pyx:48-49
+    if (mask && mask[i]) acc = -FLT_MAX;        // topk.pyx:55-56
+    out[i] = acc;
+    oid[i] = i;
+  }
+  __syncthreads();
+  if (liked_indptr)                              // topk.pyx:51-54
+    for (int p = liked_indptr[q] + threadIdx.x; p < liked_indptr[q + 1]; p += blockDim.x) out[liked_indices[p]] = -FLT_MAX;
+}
+
+__global__ void segment_offsets_kernel(int32_t *off, int n_seg, int n_items) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n_seg) off[i] = i * n_items;
+}
+
+int topk_by_sort(als_ctx *ctx, const TopkArgs &a, int ld, int32_t *ids_host, float *scores_host, int k_out) {
+  const int64_t I = a.n_items;
+  // rows per pass: keys + values, in and out, within ~1 GB and 2^31 elements
+  const int64_t per_row = I * 16;
+  const int rows_per_pass = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)a.n_query, (1ll << 30) / per_row, (int64_t)INT32_MAX / I}));
+  float *S_in = nullptr, *S_out = nullptr;
+  int32_t *V_in = nullptr, *V_out = nullptr, *off = nullptr;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+  const int64_t n = (int64_t)rows_per_pass * I;
+  cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, tmp_bytes, S_in, S_out, V_in, V_out, (int)n, rows_per_pass, off, off + 1, 0,
+                                                     32, ctx->stream);
+  ALS_CUDA(cudaMalloc(&S_in, n * 4));
+  ALS_CUDA(cudaMalloc(&S_out, n * 4));
+  ALS_CUDA(cudaMalloc(&V_in, n * 4));
+  ALS_CUDA(cudaMalloc(&V_out, n * 4));
+  ALS_CUDA(cudaMalloc(&off, (rows_per_pass + 1) * 4));
+  ALS_CUDA(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+  segment_offsets_kernel<<<(rows_per_pass + 256) / 256, 256, 0, ctx->stream>>>(off, rows_per_pass, (int)I);
+  int rc = ALS_OK;
+  std::vector<float> hs((size_t)rows_per_pass * a.k);
+  std::vector<int32_t> hi((size_t)rows_per_pass * a.k);
+  for (int q0 = 0; q0 < a.n_query && rc == ALS_OK; q0 += rows_per_pass) {
+    const int nq = std::min(rows_per_pass, a.n_query - q0);
+    ProfScope prof(ctx, kProfTopk);
+    score_rows_kernel<<<nq, 256, ld * sizeof(float), ctx->stream>>>(a.items, a.n_items, ld, a.queries, a.query_rows, q0, a.norms, a.mask,
+                                                                     a.liked_indptr, a.liked_indices, S_in, V_in);
+    cudaError_t e = cub::DeviceSegmentedRadixSort::SortPairsDescending(tmp, tmp_bytes, S_in, S_out, V_in, V_out, (int)((int64_t)nq * I), nq,
+                                                                       off, off + 1, 0, 32, ctx->stream);
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      set_error("topk: segmented sort failed (%s)", cudaGetErrorString(e));
+      rc = ALS_E_CUDA;
+      break;
+    }
+    ctx->launches += 2;
+    cudaMemcpy2DAsync(hs.data(), sizeof(float) * a.k, S_out, sizeof(float) * I, sizeof(float) * a.k, nq, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpy2DAsync(hi.data(), sizeof(int32_t) * a.k, V_out, sizeof(int32_t) * I, sizeof(int32_t) * a.k, nq, cudaMemcpyDeviceToHost,
+                      ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      set_error("topk: fallback pass failed");
+      rc = ALS_E_CUDA;
+      break;
+    }
+    for (int r = 0; r < nq; ++r) {
+      float *sr = hs.data() + (size_t)r * a.k;
+      int32_t *ir = hi.data() + (size_t)r * a.k;
+      for (int b = 0; b < a.k;) {  // runs of equal scores come out larger column first (select.h:33)
+        int e2 = b + 1;
+        while (e2 < a.k && sr[e2] == sr[b]) ++e2;
+        std::reverse(ir + b, ir + e2);
+        b = e2;
+      }
+      memcpy(scores_host + (size_t)(q0 + r) * k_out, sr, sizeof(float) * a.k);
+      memcpy(ids_host + (size_t)(q0 + r) * k_out, ir, sizeof(int32_t) * a.k);
+    }
+  }
+  cudaFree(S_in);
+  cudaFree(S_out);
+  cudaFree(V_in);
+  cudaFree(V_out);
+  cudaFree(off);
+  cudaFree(tmp);
+  return rc;
+}
+
 template <int F>
 int run_topk_f(als_ctx *ctx, const TopkArgs &a) {
   if (a.k <= 64) return run_topk<F, 4>(ctx, a);
@@ -448,6 +556,11 @@ int launch_topk(als_ctx *ctx, const als_factors *items, const als_factors *queri
   a.ids = (int32_t *)(base + o_ids);
   a.scores = (float *)(base + o_sc);
 #define CALL(FF) run_topk_f<FF>(ctx, a)
+  // k-lists of 2 * QB * k floats (QB = 16 rows per CTA beyond k = 64) must fit next to the operand tiles
+  const bool by_sort = !use_tc && k_eff > 64 && (int64_t)k_eff * 16 * 2 * 4 + 96 * 1024 > 227 * 1024;
+  if (by_sort) {
+    return topk_by_sort(ctx, a, items->ld, ids_host, scores_host, k);
+  }
   if (use_tc) {
     rc = launch_topk_tc(ctx, a.items, I, a.queries, a.query_rows, n_query, k_eff, a.mask, a.liked_indptr, a.liked_indices,
                         a.ids, a.scores, base + o_tc);

@@ -147,6 +147,13 @@ int als_whitened_factors(als_ctx *ctx, const als_factors *Y, double regularizati
 int als_gramian_shard(als_ctx *ctx, const als_factors *Y, int64_t row0, int64_t nrows);
 int als_least_squares_pregram(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
                               double regularization, int64_t *bad_row);
+/* The asynchronous flavour for the multi-GPU fit loop: queues the half and returns; a row that is not positive
+ * definite is remembered on the device and its flag rides along with the next als_gramian_shard all-reduce, so
+ * every rank learns of any rank's failure.  als_solver_status synchronises, reports (and clears) the first bad row
+ * of THIS rank since the last call (-1: none; then returns ALS_E_NOT_POSDEF) and whether any rank failed. */
+int als_least_squares_pregram_async(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
+                                    double regularization);
+int als_solver_status(als_ctx *ctx, int64_t *bad_row, int *any_rank_failed);
 int als_least_squares_cg_pregram(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y,
                                  float regularization, int cg_steps);
 
