@@ -255,6 +255,7 @@ struct BatchCfg {
   static constexpr int NPH = F / KP;
   static constexpr int LDW = 20;             // words per staged row: 8 hi + 8 lo + 4 (conflict-free fragment reads)
   static constexpr int STAGE = NS * LDW;
+  static constexpr int NST = NS <= 40 ? 3 : 2;  // stages of the W_u ring: two phases of gathers in flight where shared memory allows
   static constexpr int TRI = NS * (NS + 1) / 2;
   // the B systems of a batch start G banks apart: phase B reads them conflict free
   static constexpr int SYS = TRI + (((G - TRI % 32) % 32) + 32) % 32;
@@ -262,7 +263,7 @@ struct BatchCfg {
   __host__ __device__ static constexpr int roff(int i) { return i * NS - i * (i + 1) / 2; }
   __host__ __device__ static constexpr int off(int q) { return G * q * (q + 1) / 2; }  // registers of column block q
   static constexpr int META = B * NS;
-  static constexpr int WARP_FLOATS = 2 * STAGE + B * SYS + 3 * META + 32;
+  static constexpr int WARP_FLOATS = NST * STAGE + B * SYS + 3 * META + 32;
   static constexpr int SMEM_FLOATS = kBatchWarps * WARP_FLOATS;
   static_assert((B * NS) % 32 == 0, "prologue loop must be warp uniform");
   static_assert(WARP_FLOATS % 4 == 0 && STAGE % 2 == 0 && (B * SYS) % 4 == 0 && META % 4 == 0, "alignment");
@@ -354,8 +355,8 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   float *wsm = reinterpret_cast<float *>(short_smem) + warp * C::WARP_FLOATS;
-  uint32_t *stage = reinterpret_cast<uint32_t *>(wsm);   // 2 stages of W_u: per row 8 fp16-pair words hi, 8 lo
-  float *sys = wsm + 2 * C::STAGE;                        // B packed upper triangles
+  uint32_t *stage = reinterpret_cast<uint32_t *>(wsm);   // NST stages of W_u: per row 8 fp16-pair words hi, 8 lo
+  float *sys = wsm + C::NST * C::STAGE;                   // B packed upper triangles
   int *idxs = reinterpret_cast<int *>(sys + B * C::SYS);  // [B][NS] column indices (padding repeats a real one)
   float *es = reinterpret_cast<float *>(idxs + C::META);  // [B][NS] sqrt(|c| - 1) / 2^14, 0 on padding
   float *zs = es + C::META;                               // [B][NS] E^-1 c+, then t = E s
@@ -421,7 +422,7 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
     //      already split (dense.cu): per row and phase 8 words of fp16 pairs "hi" and 8 words "lo".
     auto issue = [&](int p) {
       const int b = p / NPH, ph = p % NPH;
-      uint32_t *st = stage + (p & 1) * C::STAGE;
+      uint32_t *st = stage + (p % C::NST) * C::STAGE;
       const int *ix = idxs + b * NS;
 #pragma unroll
       for (int q = 0; q < NT8; ++q) {
@@ -435,16 +436,19 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
 #pragma unroll
     for (int e = 0; e < C::NTILES; ++e) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
     const int TP = nb * NPH;
-    issue(0);
+    // the ring holds the phase being multiplied and NST - 1 phases of gathers in flight (empty groups past the end keep
+    // the cp.async group count uniform)
+#pragma unroll
+    for (int q = 0; q < C::NST - 1; ++q) {
+      if (q < TP) issue(q);
+      else cp_async_commit();
+    }
     for (int p = 0; p < TP; ++p) {
-      if (p + 1 < TP) {
-        issue(p + 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
+      if (p + C::NST - 1 < TP) issue(p + C::NST - 1);
+      else cp_async_commit();
+      cp_async_wait<C::NST - 1>();
       __syncwarp();
-      const uint32_t *sg = stage + (p & 1) * C::STAGE;
+      const uint32_t *sg = stage + (p % C::NST) * C::STAGE;
       {
         uint32_t h0[NT8], h1[NT8], l0[NT8], l1[NT8];
 #pragma unroll
@@ -498,7 +502,7 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
           }
         }
       }
-      __syncwarp();  // the stage is free for phase p + 2
+      __syncwarp();  // the stage is free for phase p + NST
     }
 
     // ---- phase B: all systems of the batch at once, G lanes per system
@@ -526,45 +530,94 @@ short_batch_kernel(const int32_t *__restrict__ indices, const float *__restrict_
 
     // ---- phase C: x = Z_u^T t, lane owns columns 2 lane, 2 lane + 1
     const bool owns = 2 * lane < F;
-    for (int b = 0; b < nb; ++b) {
-      if (__shfl_sync(kFull, (int)my_defer, b)) continue;
-      const int row = __shfl_sync(kFull, mine.row, b);
-      const int n = __shfl_sync(kFull, my_n, b);
+    auto store_x = [&](int row, float x0, float x1) {
       const int64_t xoff = (row_offset + row) * F;
-      float x0 = 0.f, x1 = 0.f;  // no observations: the reference zeroes the row (_als.pyx:98-100)
-      const int *ix = idxs + b * NS;
-      const float *tv = zs + b * NS;
-      // all NS slots are gathered, 16 loads in flight at a time: the padding has t = 0 and repeats a valid index, and
-      // unconditional loads let the whole chunk be issued before the first use (one latency exposure per 16 rows of Z)
-#pragma unroll
-      for (int i0 = 0; i0 < NS; i0 += 16) {
-        constexpr int kMaxChunk = 16;
-        const int cn = NS - i0 < kMaxChunk ? NS - i0 : kMaxChunk;  // 16 or 8 (compile time after unrolling)
-        if (i0 >= n) break;                                        // warp uniform
-        int id[kMaxChunk];
-        float tt[kMaxChunk];
-#pragma unroll
-        for (int u = 0; u < kMaxChunk; u += 4)
-          if (u < cn) {
-            const int4 iv = *reinterpret_cast<const int4 *>(ix + i0 + u);
-            const float4 tv4 = *reinterpret_cast<const float4 *>(tv + i0 + u);
-            id[u] = iv.x; id[u + 1] = iv.y; id[u + 2] = iv.z; id[u + 3] = iv.w;
-            tt[u] = tv4.x; tt[u + 1] = tv4.y; tt[u + 2] = tv4.z; tt[u + 3] = tv4.w;
-          }
-        float2 zz[kMaxChunk];
-#pragma unroll
-        for (int u = 0; u < kMaxChunk; ++u)
-          if (u < cn) zz[u] = owns ? __ldcg(reinterpret_cast<const float2 *>(Z + (int64_t)id[u] * F) + lane) : make_float2(0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < kMaxChunk; ++u)
-          if (u < cn) {
-            x0 = fmaf(tt[u], zz[u].x, x0);
-            x1 = fmaf(tt[u], zz[u].y, x1);
-          }
-      }
       if (owns) {
         *reinterpret_cast<float2 *>(X + xoff + 2 * lane) = make_float2(x0, x1);
         for (int pi = 0; pi < n_peers; ++pi) *reinterpret_cast<float2 *>(peers[pi] + xoff + 2 * lane) = make_float2(x0, x1);
+      }
+    };
+    if constexpr (NS <= 40) {
+      // The rows of Z of system b + 1 are gathered (cp.async) into the shared memory that the W_u ring and the solved
+      // systems no longer need while system b is reduced: one exposed gather latency per BATCH instead of per row.
+      constexpr int CH = F / 4, RPI = 32 / CH;  // 16-byte chunks per row of Z, rows per warp-wide copy
+      static_assert(C::NST * C::STAGE + B * C::SYS >= 2 * NS * F, "phase C double buffer does not fit");
+      float *zbuf = wsm;
+      auto zissue = [&](int b, int buf) {
+        const int n = __shfl_sync(kFull, my_n, b);
+        const bool skip = __shfl_sync(kFull, (int)my_defer, b) != 0;
+        if (!skip) {
+          const int *ix = idxs + b * NS;
+          const int r = lane / CH, ch = lane % CH;
+          for (int i = 0; i < n; i += RPI)  // the padding up to the class size repeats a valid index
+            if (r < RPI && i + r < NS)
+              cp_async16(zbuf + (buf * NS + i + r) * F + 4 * ch, Z + (int64_t)ix[i + r] * F + 4 * ch);
+        }
+        cp_async_commit();
+      };
+      zissue(0, 0);
+      for (int b = 0; b < nb; ++b) {
+        if (b + 1 < nb) zissue(b + 1, (b + 1) & 1);
+        else cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        if (!__shfl_sync(kFull, (int)my_defer, b)) {
+          const int row = __shfl_sync(kFull, mine.row, b);
+          const int n = __shfl_sync(kFull, my_n, b);
+          const float *zb = zbuf + (b & 1) * NS * F + 2 * lane;
+          const float *tv = zs + b * NS;
+          float x0 = 0.f, x1 = 0.f;  // no observations: the reference zeroes the row (_als.pyx:98-100)
+          for (int i = 0; i < n; i += 4) {  // t = 0 on the padding (and its rows were gathered whenever i + r < NS)
+            const float4 t4 = *reinterpret_cast<const float4 *>(tv + i);
+            const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i + u < n && owns) {
+                const float2 z2 = *reinterpret_cast<const float2 *>(zb + (i + u) * F);
+                x0 = fmaf(tt[u], z2.x, x0);
+                x1 = fmaf(tt[u], z2.y, x1);
+              }
+          }
+          store_x(row, x0, x1);
+        }
+        __syncwarp();  // the buffer is free for system b + 2
+      }
+    } else {
+      for (int b = 0; b < nb; ++b) {
+        if (__shfl_sync(kFull, (int)my_defer, b)) continue;
+        const int row = __shfl_sync(kFull, mine.row, b);
+        const int n = __shfl_sync(kFull, my_n, b);
+        float x0 = 0.f, x1 = 0.f;
+        const int *ix = idxs + b * NS;
+        const float *tv = zs + b * NS;
+        // all NS slots are gathered, 16 loads in flight at a time: the padding has t = 0 and repeats a valid index
+#pragma unroll
+        for (int i0 = 0; i0 < NS; i0 += 16) {
+          constexpr int kMaxChunk = 16;
+          const int cn = NS - i0 < kMaxChunk ? NS - i0 : kMaxChunk;  // 16 or 8 (compile time after unrolling)
+          if (i0 >= n) break;                                        // warp uniform
+          int id[kMaxChunk];
+          float tt[kMaxChunk];
+#pragma unroll
+          for (int u = 0; u < kMaxChunk; u += 4)
+            if (u < cn) {
+              const int4 iv = *reinterpret_cast<const int4 *>(ix + i0 + u);
+              const float4 tv4 = *reinterpret_cast<const float4 *>(tv + i0 + u);
+              id[u] = iv.x; id[u + 1] = iv.y; id[u + 2] = iv.z; id[u + 3] = iv.w;
+              tt[u] = tv4.x; tt[u + 1] = tv4.y; tt[u + 2] = tv4.z; tt[u + 3] = tv4.w;
+            }
+          float2 zz[kMaxChunk];
+#pragma unroll
+          for (int u = 0; u < kMaxChunk; ++u)
+            if (u < cn) zz[u] = owns ? __ldcg(reinterpret_cast<const float2 *>(Z + (int64_t)id[u] * F) + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < kMaxChunk; ++u)
+            if (u < cn) {
+              x0 = fmaf(tt[u], zz[u].x, x0);
+              x1 = fmaf(tt[u], zz[u].y, x1);
+            }
+        }
+        store_x(row, x0, x1);
       }
     }
   }

@@ -364,24 +364,36 @@ int run_topk(als_ctx *ctx, const TopkArgs &a) {
   return ALS_OK;
 }
 
-// ---- very large k (the k-lists no longer fit in shared memory): scores to HBM, one stable segmented sort --------
+// ---- very large k (the k-lists no longer fit in shared memory): scores to HBM, one segmented sort ---------------
 // rank_items / recommend with N in the thousands up to "all items" (the reference's select.h takes any k).  One CTA per
-// query row writes the filtered score row (fp32 FMA dot products), cub sorts every row descending by score (stable:
-// equal scores keep ascending item order, so the boundary of the first k prefers the smaller column like select.h:23),
-// and the host reverses each run of equal scores (select.h:33 emits larger columns first).
+// query row writes a 64-bit sort key per item -- the score in its order-preserving integer form above a tie-breaker
+// that reproduces the reference's heap on ties -- and cub sorts every row descending:
+//   * unfiltered items: tie-breaker ~id, so equal scores come out smaller column first and the boundary of the
+//     first k prefers the smaller column (select.h:23 admits only strictly better scores); the host then reverses
+//     each run of equal scores (select.h:33 emits larger columns first);
+//   * filtered items all tie at -FLT_MAX, and there the heap's history matters: the first k columns fill it, later
+//     (better) items evict the smallest column first and later filtered columns never enter, so the survivors are the
+//     LARGEST filtered columns below k: tie-breaker id + 1 for id < k, 0 beyond (never selected), already in
+//     output order.
 __global__ void __launch_bounds__(256) score_rows_kernel(const float *__restrict__ items, int n_items, int ld,
                                                          const float *__restrict__ queries, const int32_t *__restrict__ query_rows,
-                                                         int q0, const float *__restrict__ norms, const uint8_t *__restrict__ mask,
-                                                         const int32_t *__restrict__ liked_indptr,
-                                                         const int32_t *__restrict__ liked_indices, float *__restrict__ S,
-                                                         int32_t *__restrict__ ids) {
+                                                         int q0, int k, const float *__restrict__ norms,
+                                                         const uint8_t *__restrict__ mask, const int32_t *__restrict__ liked_indptr,
+                                                         const int32_t *__restrict__ liked_indices,
+                                                         unsigned long long *__restrict__ keys, int32_t *__restrict__ ids) {
   extern __shared__ float qrow[];
   const int q = q0 + blockIdx.x;
   const int64_t src = query_rows ? query_rows[q] : q;
   for (int j = threadIdx.x; j < ld; j += blockDim.x) qrow[j] = queries[src * ld + j];
   __syncthreads();
-  float *out = S + (int64_t)blockIdx.x * n_items;
+  unsigned long long *out = keys + (int64_t)blockIdx.x * n_items;
   int32_t *oid = ids + (int64_t)blockIdx.x * n_items;
+  auto key_of = [&](float sc, int i, bool filtered) -> unsigned long long {
+    const unsigned b = __float_as_uint(sc);
+    const unsigned ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotone map of floats onto unsigned integers
+    const unsigned tie = filtered ? (i < k ? (unsigned)i + 1u : 0u) : ~(unsigned)i;
+    return ((unsigned long long)ord << 32) | tie;
+  };
   for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
     const float4 *it = reinterpret_cast<const float4 *>(items + (int64_t)i * ld);
     float acc = 0.f;
@@ -390,13 +402,16 @@ __global__ void __launch_bounds__(256) score_rows_kernel(const float *__restrict
       acc = fmaf(v.x, qrow[4 * j], fmaf(v.y, qrow[4 * j + 1], fmaf(v.z, qrow[4 * j + 2], fmaf(v.w, qrow[4 * j + 3], acc))));
     }
     if (norms) acc /= norms[i];                 // topk.pyx:48-49
-    if (mask && mask[i]) acc = -FLT_MAX;        // topk.pyx:55-56
-    out[i] = acc;
+    const bool filtered = mask && mask[i];      // topk.pyx:55-56
+    out[i] = key_of(filtered ? -FLT_MAX : acc, i, filtered);
     oid[i] = i;
   }
   __syncthreads();
   if (liked_indptr)                              // topk.pyx:51-54
-    for (int p = liked_indptr[q] + threadIdx.x; p < liked_indptr[q + 1]; p += blockDim.x) out[liked_indices[p]] = -FLT_MAX;
+    for (int p = liked_indptr[q] + threadIdx.x; p < liked_indptr[q + 1]; p += blockDim.x) {
+      const int i = liked_indices[p];
+      out[i] = key_of(-FLT_MAX, i, true);
+    }
 }
 
 __global__ void segment_offsets_kernel(int32_t *off, int n_seg, int n_items) {
@@ -406,40 +421,41 @@ __global__ void segment_offsets_kernel(int32_t *off, int n_seg, int n_items) {
 
 int topk_by_sort(als_ctx *ctx, const TopkArgs &a, int ld, int32_t *ids_host, float *scores_host, int k_out) {
   const int64_t I = a.n_items;
-  // rows per pass: keys + values, in and out, within ~1 GB and 2^31 elements
-  const int64_t per_row = I * 16;
-  const int rows_per_pass = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)a.n_query, (1ll << 30) / per_row, (int64_t)INT32_MAX / I}));
-  float *S_in = nullptr, *S_out = nullptr;
+  // rows per pass: keys + values, in and out, within ~1.5 GB and 2^31 elements
+  const int64_t per_row = I * 24;
+  const int rows_per_pass =
+      (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)a.n_query, (3ll << 29) / per_row, (int64_t)INT32_MAX / I}));
+  unsigned long long *K_in = nullptr, *K_out = nullptr;
   int32_t *V_in = nullptr, *V_out = nullptr, *off = nullptr;
   void *tmp = nullptr;
   size_t tmp_bytes = 0;
   const int64_t n = (int64_t)rows_per_pass * I;
-  cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, tmp_bytes, S_in, S_out, V_in, V_out, (int)n, rows_per_pass, off, off + 1, 0,
-                                                     32, ctx->stream);
-  ALS_CUDA(cudaMalloc(&S_in, n * 4));
-  ALS_CUDA(cudaMalloc(&S_out, n * 4));
+  cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, tmp_bytes, K_in, K_out, V_in, V_out, (int)n, rows_per_pass, off, off + 1, 0,
+                                                     64, ctx->stream);
+  ALS_CUDA(cudaMalloc(&K_in, n * 8));
+  ALS_CUDA(cudaMalloc(&K_out, n * 8));
   ALS_CUDA(cudaMalloc(&V_in, n * 4));
   ALS_CUDA(cudaMalloc(&V_out, n * 4));
   ALS_CUDA(cudaMalloc(&off, (rows_per_pass + 1) * 4));
   ALS_CUDA(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
   segment_offsets_kernel<<<(rows_per_pass + 256) / 256, 256, 0, ctx->stream>>>(off, rows_per_pass, (int)I);
   int rc = ALS_OK;
-  std::vector<float> hs((size_t)rows_per_pass * a.k);
+  std::vector<unsigned long long> hk((size_t)rows_per_pass * a.k);
   std::vector<int32_t> hi((size_t)rows_per_pass * a.k);
   for (int q0 = 0; q0 < a.n_query && rc == ALS_OK; q0 += rows_per_pass) {
     const int nq = std::min(rows_per_pass, a.n_query - q0);
     ProfScope prof(ctx, kProfTopk);
-    score_rows_kernel<<<nq, 256, ld * sizeof(float), ctx->stream>>>(a.items, a.n_items, ld, a.queries, a.query_rows, q0, a.norms, a.mask,
-                                                                     a.liked_indptr, a.liked_indices, S_in, V_in);
-    cudaError_t e = cub::DeviceSegmentedRadixSort::SortPairsDescending(tmp, tmp_bytes, S_in, S_out, V_in, V_out, (int)((int64_t)nq * I), nq,
-                                                                       off, off + 1, 0, 32, ctx->stream);
+    score_rows_kernel<<<nq, 256, ld * sizeof(float), ctx->stream>>>(a.items, a.n_items, ld, a.queries, a.query_rows, q0, a.k, a.norms,
+                                                                     a.mask, a.liked_indptr, a.liked_indices, K_in, V_in);
+    cudaError_t e = cub::DeviceSegmentedRadixSort::SortPairsDescending(tmp, tmp_bytes, K_in, K_out, V_in, V_out, (int)((int64_t)nq * I), nq,
+                                                                       off, off + 1, 0, 64, ctx->stream);
     if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
       set_error("topk: segmented sort failed (%s)", cudaGetErrorString(e));
       rc = ALS_E_CUDA;
       break;
     }
     ctx->launches += 2;
-    cudaMemcpy2DAsync(hs.data(), sizeof(float) * a.k, S_out, sizeof(float) * I, sizeof(float) * a.k, nq, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpy2DAsync(hk.data(), 8 * (size_t)a.k, K_out, 8 * (size_t)I, 8 * (size_t)a.k, nq, cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpy2DAsync(hi.data(), sizeof(int32_t) * a.k, V_out, sizeof(int32_t) * I, sizeof(int32_t) * a.k, nq, cudaMemcpyDeviceToHost,
                       ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -448,20 +464,25 @@ int topk_by_sort(als_ctx *ctx, const TopkArgs &a, int ld, int32_t *ids_host, flo
       break;
     }
     for (int r = 0; r < nq; ++r) {
-      float *sr = hs.data() + (size_t)r * a.k;
+      const unsigned long long *kr = hk.data() + (size_t)r * a.k;
       int32_t *ir = hi.data() + (size_t)r * a.k;
+      float *sr = scores_host + (size_t)(q0 + r) * k_out;
+      for (int j = 0; j < a.k; ++j) {
+        const unsigned ord = (unsigned)(kr[j] >> 32);
+        const unsigned b = (ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord;
+        memcpy(&sr[j], &b, sizeof(float));
+      }
       for (int b = 0; b < a.k;) {  // runs of equal scores come out larger column first (select.h:33)
         int e2 = b + 1;
         while (e2 < a.k && sr[e2] == sr[b]) ++e2;
-        std::reverse(ir + b, ir + e2);
+        if (sr[b] != -FLT_MAX) std::reverse(ir + b, ir + e2);  // the filtered tail is already in output order
         b = e2;
       }
-      memcpy(scores_host + (size_t)(q0 + r) * k_out, sr, sizeof(float) * a.k);
       memcpy(ids_host + (size_t)(q0 + r) * k_out, ir, sizeof(int32_t) * a.k);
     }
   }
-  cudaFree(S_in);
-  cudaFree(S_out);
+  cudaFree(K_in);
+  cudaFree(K_out);
   cudaFree(V_in);
   cudaFree(V_out);
   cudaFree(off);

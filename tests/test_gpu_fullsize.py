@@ -94,13 +94,24 @@ def test_c2_three_iteration_fit_matches_oracle(lib, ctx, orc, c2):
     m.fit(Cui, show_progress=False)
     eu, ei = row_err(m.user_factors, Xe), row_err(m.item_factors, Ye)
     e = np.concatenate([eu, ei])
+    # How far apart do two CORRECT fp32 runs end up after three iterations from this cold start (condition number
+    # ~2e2 in the first half)?  The reference against itself from initial factors perturbed in the last bit measures
+    # it; the GPU fit must sit within a small multiple of that, and within 1e-4 wherever the reference is that stable.
+    rng = np.random.default_rng(98)
+    Xp = (X0 * (1 + 1e-7 * rng.standard_normal(X0.shape))).astype(np.float32)
+    Yp = (Y0 * (1 + 1e-7 * rng.standard_normal(Y0.shape))).astype(np.float32)
+    oracle.fit(Cui, Xp, Yp, regularization=0.01, iterations=3, use_cg=False, kind=orc.name)
+    eself = np.concatenate([row_err(Xp, Xe), row_err(Yp, Ye)])
     print(f"C2 3-iteration fit, all {len(e)} rows: users max {eu.max():.2e} median {np.median(eu):.2e}; items max {ei.max():.2e} "
-          f"median {np.median(ei):.2e}; rows above 1e-4: {(e > CHOL_MAX).sum()}")
-    # three iterations from the cold start: the first half has condition number ~2e2 and fp32 LAPACK itself is ~1e-4
-    # from the fp64 solution on its worst rows (test_gpu_parity.py::test_c2_full_size...), which the next halves inherit
-    assert np.median(e) < 1e-5
-    assert np.quantile(e, 0.999) < CHOL_MAX
-    assert e.max() < 5e-4
+          f"median {np.median(ei):.2e}; rows above 1e-4: {(e > CHOL_MAX).sum()}; reference vs itself from 1e-7-perturbed "
+          f"factors: max {eself.max():.2e} p99.9 {np.quantile(eself, 0.999):.2e} median {np.median(eself):.2e}")
+    assert np.median(e) < max(1e-5, 3 * np.median(eself))
+    assert np.quantile(e, 0.999) < max(CHOL_MAX, 3 * np.quantile(eself, 0.999))
+    assert e.max() < max(5e-4, 3 * eself.max())
+    loss_g = orc.calculate_loss(Cui, np.ascontiguousarray(m.user_factors), np.ascontiguousarray(m.item_factors), 0.01)
+    loss_e = orc.calculate_loss(Cui, Xe, Ye, 0.01)
+    print(f"   training loss: GPU factors {loss_g:.7f}, reference factors {loss_e:.7f}")
+    assert abs(loss_g - loss_e) < 1e-4 * abs(loss_e)
 
 
 # ---------------------------------------------------------------------------------------- C3
@@ -285,8 +296,9 @@ def test_topk_very_large_k_falls_back_to_a_full_sort(lib, ctx, orc):
     for h in (dl, dq, di):
         h.close()
     eids, esc = orc.topk(items, users, k, filter_query_items=liked, filter_items=flt)
-    live = esc > -1e38  # among the filtered tail every score ties at -FLT_MAX: only its membership is defined
+    live = esc > -1e38
     np.testing.assert_allclose(sc, esc, rtol=2e-5, atol=1e-5)
     assert (ids[live] == eids[live]).mean() > 0.999
-    for r in range(Q):
-        assert set(ids[r][~live[r]]) == set(eids[r][~live[r]])
+    # the filtered tail ties at -FLT_MAX: which of those items survive and in what order is pure heap semantics
+    # (select.h: the first k columns fill the heap, later better items evict the smallest column first)
+    np.testing.assert_array_equal(ids[~live], eids[~live])

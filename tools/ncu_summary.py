@@ -47,8 +47,13 @@ def main():
             if len(r) < len(h):
                 continue
             toks = r[ix["Source"]].split()
+            if not toks:
+                continue
             op = (toks[1] if toks[0].startswith("@") else toks[0]).split(".")[0]
-            n, s = int(r[ix["Instructions Executed"]]), int(r[ix["# Samples"]])
+            try:  # reports with several kernels repeat the header rows per kernel
+                n, s = int(r[ix["Instructions Executed"]]), int(r[ix["# Samples"]])
+            except ValueError:
+                continue
             by_op[op] += n
             st_op[op] += s
             tot += n
