@@ -198,7 +198,8 @@ def run_reference(args):
         return
     from implicit_b200 import synthetic
 
-    Cui, X0, Y0, cfg = synthetic.config(args.config, scale=args.scale)
+    ref_scale = args.scale * (0.02 if args.config == "C4" else 1.0)  # C4: a 1/50 instance of the same recipe on the host
+    Cui, X0, Y0, cfg = synthetic.config(args.config, scale=ref_scale)
     rates = []
     for _ in range(args.warmup):
         cpu_reference_rate(Cui, X0, Y0, cfg, seconds=1.0)
@@ -238,20 +239,39 @@ def run_ours(args):
 
     pg = init_process_group()
     rank, world, ctx = pg.rank, pg.world, pg.ctx
-    Cui_host, X0, Y0, cfg = synthetic.config(args.config, scale=args.scale)
+    on_device = args.config == "C4"  # 10M x 1M, 500M nnz: generated on the device (csrc/gen.cu), identically on every rank
+    if on_device:
+        cfg = dict(synthetic.CONFIGS["C4"])
+        cfg.update(users=max(8, int(cfg["users"] * args.scale)), items=max(8, int(cfg["items"] * args.scale)),
+                   nnz=max(8, int(cfg["nnz"] * args.scale)))
+        Cui_host = X0 = Y0 = None
+    else:
+        Cui_host, X0, Y0, cfg = synthetic.config(args.config, scale=args.scale)
     users, items, f = cfg["users"], cfg["items"], cfg["factors"]
     use_cg = cfg["use_cg"]
     reg = 0.01
 
+    def initial_factors_on_device():
+        if on_device:
+            A, B = _lib.DeviceFactors(ctx, users, f), _lib.DeviceFactors(ctx, items, f)
+            A.fill_uniform(42, 0.01)   # the distribution of implicit/cpu/als.py:144-147, hashed instead of PCG64
+            B.fill_uniform(43, 0.01)
+            return A, B
+        return _lib.DeviceFactors.from_host(ctx, X0), _lib.DeviceFactors.from_host(ctx, Y0)
+
     # ---- device-resident arm
-    Cui = _lib.DeviceCSR.upload(ctx, Cui_host)
+    if on_device:
+        Cui = _lib.DeviceCSR.generate(ctx, users, items, cfg["nnz"], cfg["seed"])
+        cfg["nnz"] = int(Cui.shape3[2])
+    else:
+        Cui = _lib.DeviceCSR.upload(ctx, Cui_host)
     Ciu = Cui.transpose()
-    X, Y = _lib.DeviceFactors.from_host(ctx, X0), _lib.DeviceFactors.from_host(ctx, Y0)
+    X, Y = initial_factors_on_device()
     Cui_s, Ciu_s, usplit, isplit = Cui, Ciu, None, None
     p2p = world > 1 and os.environ.get("ALS_B200_NO_P2P") != "1"
     if world > 1:
         row_cost = 20 if use_cg else 60
-        usplit = nnz_balanced_splits(Cui_host.indptr, world, row_cost)
+        usplit = nnz_balanced_splits(Cui.indptr_host() if on_device else Cui_host.indptr, world, row_cost)
         isplit = nnz_balanced_splits(Ciu.indptr_host(), world, row_cost)
         Cui_s = Cui.slice_rows(usplit[rank], usplit[rank + 1])
         Ciu_s = Ciu.slice_rows(isplit[rank], isplit[rank + 1])
@@ -279,6 +299,7 @@ def run_ours(args):
         half(Ciu_s, Y, X, isplit)
 
     flush = cfg["nnz"] * 8 <= 126e6  # small debug scales fit in L2: flush it between iterations
+    scaling = "weak" if on_device else "strong"  # C4 is the configuration sized for 8 GPUs; C2 / C3 are fixed problems
     for _ in range(max(args.warmup, 3)):
         iteration()
     ctx.sync()
@@ -317,7 +338,7 @@ def run_ours(args):
         total_iters = max(args.warmup, 3) + args.steps
         xs, ys = X.download(), Y.download()
         if rank == 0:
-            X1, Y1 = _lib.DeviceFactors.from_host(ctx, X0), _lib.DeviceFactors.from_host(ctx, Y0)
+            X1, Y1 = initial_factors_on_device()
             for _ in range(total_iters):
                 if use_cg:
                     _lib.least_squares_cg(ctx, Cui, X1, Y1, reg, 3)
@@ -367,6 +388,11 @@ def run_ours(args):
     #      arrays (pageable memory), which is what a user of the reference passes to fit(); secondary: the same
     #      arrays already page-locked (what a serving loop that re-fits from a staging buffer would hold).
     e2e = None
+    if on_device and not args.no_e2e:
+        # host copies of the device-generated inputs, for the public-API arm (fit() takes host arrays)
+        Cui_host = Cui.download()
+        X0, Y0 = initial_factors_on_device()
+        X0, Y0 = (lambda a, b: (a.download(), b.download()))(X0, Y0)
     if not args.no_e2e:
         def timed_fits(Cin, X0in, Y0in, reps):
             times = []
@@ -403,7 +429,7 @@ def run_ours(args):
 
         h2d = Cui_host.data.nbytes + Cui_host.indices.nbytes + Cui_host.indptr.nbytes + X0.nbytes + Y0.nbytes
         d2h = X0.nbytes + Y0.nbytes
-        reps = max(3, min(7, args.steps))
+        reps = 2 if on_device else max(3, min(7, args.steps))
         times = timed_fits(Cui_host, X0, Y0, reps)
         Cpin = pinned_csr(Cui_host)
         X0p, Y0p = _lib.pinned_empty(X0.shape, np.float32), _lib.pinned_empty(Y0.shape, np.float32)
@@ -421,13 +447,15 @@ def run_ours(args):
                                  "fits_ms": [round(1e3 * x, 2) for x in times_pinned]}}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not on_device:
         cpu = cpu_reference_rate(Cui_host, X0, Y0, cfg, seconds=args.cpu_seconds)
 
     if rank == 0:
         out = {
             "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "note_c4": ("inputs generated on the device (csrc/gen.cu), statistically equivalent to the host generator"
+                        if on_device else None),
             "dtype": "f32 (tensor-core accumulation with 3-term hi/lo splits, fp32-faithful)", "data": "synthetic",
             "config": workload_config(cfg, args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "parity_vs_n1": parity_vs_n1,

@@ -44,6 +44,8 @@ SIGNATURES = {
     "als_host_free": (c_int, [c_void_p]),
     "als_csr_upload": (c_int, [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_i64, P(c_void_p)]),
     "als_csr_transpose": (c_int, [c_void_p, c_void_p, P(c_void_p)]),
+    "als_csr_generate": (c_int, [c_void_p, c_i64, c_i64, c_i64, ctypes.c_uint64, P(c_void_p)]),
+    "als_factors_fill_uniform": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_float]),
     "als_csr_slice_rows": (c_int, [c_void_p, c_void_p, c_i64, c_i64, P(c_void_p)]),
     "als_csr_scale": (c_int, [c_void_p, c_void_p, c_f32]),
     "als_csr_shape": (c_int, [c_void_p, P(c_i64), P(c_i64), P(c_i64)]),
@@ -309,6 +311,13 @@ class DeviceCSR:
         check(self.ctx.lib.als_csr_transpose(self.ctx.h, self.h, ctypes.byref(h)))
         return DeviceCSR(self.ctx, h)
 
+    @classmethod
+    def generate(cls, ctx, rows, cols, nnz, seed):
+        """Power-law CSR built on the device (csrc/gen.cu): for configurations too large for the host generator."""
+        h = c_void_p()
+        check(ctx.lib.als_csr_generate(ctx.h, int(rows), int(cols), int(nnz), int(seed), ctypes.byref(h)))
+        return cls(ctx, h)
+
     def slice_rows(self, r0, r1):
         h = c_void_p()
         check(self.ctx.lib.als_csr_slice_rows(self.ctx.h, self.h, int(r0), int(r1), ctypes.byref(h)))
@@ -370,6 +379,10 @@ class DeviceFactors:
         a = np.ascontiguousarray(a, dtype=np.float32)
         assert a.ndim == 2 and a.shape[1] == self.factors
         check(self.ctx.lib.als_factors_upload(self.ctx.h, self.h, ptr(a), int(row0), a.shape[0]))
+
+    def fill_uniform(self, seed, scale):
+        """factors = scale * U[0,1) generated on the device (the distribution of implicit/cpu/als.py:144-147)."""
+        check(self.ctx.lib.als_factors_fill_uniform(self.ctx.h, self.h, int(seed), float(scale)))
 
     def has_nan(self):
         flag = c_int(0)

@@ -121,7 +121,8 @@ static int h2d_copy(als_ctx *ctx, void *dst, const void *src, size_t bytes) {
   for (int t = 0; t < kStageThreads; ++t) {
     pool.emplace_back([=, &status]() {
       cudaSetDevice(ctx->device);
-      cudaError_t e = cudaSuccess;
+      // the staging buffers are shared by consecutive calls: a previous call's last DMAs may still be reading them
+      cudaError_t e = cudaStreamSynchronize(ctx->stage_stream[t]);
       int use = 0;
       for (size_t c = t; c < nchunks && e == cudaSuccess; c += kStageThreads, ++use) {
         const int b = use & 1;
@@ -557,6 +558,20 @@ ALS_API int als_csr_upload(als_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz
   }
   *out = c;
   return ALS_OK;
+}
+
+ALS_API int als_csr_generate(als_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz_target, uint64_t seed, als_csr **out) {
+  ALS_REQUIRE(ctx && out, "als_csr_generate: NULL argument");
+  ALS_REQUIRE(rows > 0 && cols > 0 && nnz_target > 0, "als_csr_generate: empty shape");
+  *out = nullptr;
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  return als::csr_generate_power_law(ctx, rows, cols, nnz_target, seed, out);
+}
+
+ALS_API int als_factors_fill_uniform(als_ctx *ctx, als_factors *f, uint64_t seed, float scale) {
+  ALS_REQUIRE(ctx && f, "als_factors_fill_uniform: NULL argument");
+  ALS_CUDA(cudaSetDevice(ctx->device));
+  return als::factors_fill_uniform(ctx, f, seed, scale);
 }
 
 ALS_API int als_csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out) {

@@ -190,6 +190,9 @@ int ensure_device_buffer(als_ctx *ctx, void **buf, int64_t *cap, int64_t bytes);
 int ensure_pinned(als_ctx *ctx, int64_t bytes);
 int build_schedule(als_ctx *ctx, als_csr *csr, const int32_t *indptr_host);
 int csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out);
+// synthetic inputs generated on the device (gen.cu)
+int csr_generate_power_law(als_ctx *ctx, int64_t users, int64_t items, int64_t nnz_target, uint64_t seed, als_csr **out);
+int factors_fill_uniform(als_ctx *ctx, als_factors *f, uint64_t seed, float scale);
 
 // kernels' host launchers (each returns an ALS_* code)
 int launch_gramian(als_ctx *ctx, const als_factors *Y);                  // -> ctx->G

@@ -91,6 +91,14 @@ int als_host_free(void *ptr);
  * Replaces CSRMatrix::CSRMatrix(rows, cols, nonzeros, indptr, indices, data), implicit/gpu/matrix.cu:222-251. */
 int als_csr_upload(als_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz, const int32_t *indptr,
                    const int32_t *indices, const float *data, int64_t row_offset, als_csr **out);
+/* Synthetic inputs generated on the device (BASELINE.json configs too large to build on the host, e.g. C4:
+ * 10M x 1M, 500M nonzeros): the power-law CSR recipe of SURVEY.md section 8(d) with counter-based hashing
+ * (deterministic per seed, statistically equivalent to implicit_b200/synthetic.py, not bit-identical), and
+ * factors = scale * U[0,1) like the reference's initialisation (implicit/cpu/als.py:144-147).
+ * (No reference equivalent: it reads datasets from disk, implicit/datasets/.) */
+int als_csr_generate(als_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz_target, uint64_t seed, als_csr **out);
+int als_factors_fill_uniform(als_ctx *ctx, als_factors *f, uint64_t seed, float scale);
+
 /* Device transpose: out = in^T as CSR (replaces the host `Cui.T.tocsr()`, implicit/cpu/als.py:137).
  * Asynchronous: the launch schedule of `out` is built at the first solve that uses it. */
 int als_csr_transpose(als_ctx *ctx, const als_csr *in, als_csr **out);

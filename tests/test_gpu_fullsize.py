@@ -87,28 +87,38 @@ def test_c2_three_iteration_fit_matches_oracle(lib, ctx, orc, c2):
     from implicit_b200 import AlternatingLeastSquares
 
     Cui, X0, Y0, cfg = c2
+    # The reference twice, concurrently (its OpenMP loops release the GIL): in fp32 -- what the GPU has to match -- and
+    # in fp64 (the `floating` fused type of _als.pyx:76-77), which is the ground truth both are measured against.  Three
+    # iterations from this cold start (condition number ~2e2 in the first half, the reference's own sgemm Gramian off
+    # by 1e-6) amplify every rounding difference ~50x, so "as close to the fp64 fit as the reference itself" is the bar
+    # that means something; the row-by-row distance to the reference and the training loss are reported and bounded too.
+    from concurrent.futures import ThreadPoolExecutor
+
     Xe, Ye = X0.copy(), Y0.copy()
-    oracle.fit(Cui, Xe, Ye, regularization=0.01, iterations=3, use_cg=False, kind=orc.name)
+    Xt, Yt = X0.astype(np.float64), Y0.astype(np.float64)
+    pool = ThreadPoolExecutor(2)
+    jobs = [pool.submit(oracle.fit, Cui, a, b, regularization=0.01, iterations=3, use_cg=False, kind=orc.name)
+            for a, b in ((Xe, Ye), (Xt, Yt))]
     m = AlternatingLeastSquares(factors=64, regularization=0.01, use_cg=False, iterations=3)
     m.user_factors, m.item_factors = X0.copy(), Y0.copy()
     m.fit(Cui, show_progress=False)
-    eu, ei = row_err(m.user_factors, Xe), row_err(m.item_factors, Ye)
-    e = np.concatenate([eu, ei])
-    # How far apart do two CORRECT fp32 runs end up after three iterations from this cold start (condition number
-    # ~2e2 in the first half)?  The reference against itself from initial factors perturbed in the last bit measures
-    # it; the GPU fit must sit within a small multiple of that, and within 1e-4 wherever the reference is that stable.
-    rng = np.random.default_rng(98)
-    Xp = (X0 * (1 + 1e-7 * rng.standard_normal(X0.shape))).astype(np.float32)
-    Yp = (Y0 * (1 + 1e-7 * rng.standard_normal(Y0.shape))).astype(np.float32)
-    oracle.fit(Cui, Xp, Yp, regularization=0.01, iterations=3, use_cg=False, kind=orc.name)
-    eself = np.concatenate([row_err(Xp, Xe), row_err(Yp, Ye)])
-    print(f"C2 3-iteration fit, all {len(e)} rows: users max {eu.max():.2e} median {np.median(eu):.2e}; items max {ei.max():.2e} "
-          f"median {np.median(ei):.2e}; rows above 1e-4: {(e > CHOL_MAX).sum()}; reference vs itself from 1e-7-perturbed "
-          f"factors: max {eself.max():.2e} p99.9 {np.quantile(eself, 0.999):.2e} median {np.median(eself):.2e}")
-    assert np.median(e) < max(1e-5, 3 * np.median(eself))
-    assert np.quantile(e, 0.999) < max(CHOL_MAX, 3 * np.quantile(eself, 0.999))
-    assert e.max() < max(5e-4, 3 * eself.max())
-    loss_g = orc.calculate_loss(Cui, np.ascontiguousarray(m.user_factors), np.ascontiguousarray(m.item_factors), 0.01)
+    for j in jobs:
+        j.result()
+    gx, gy = np.array(m.user_factors), np.array(m.item_factors)
+    e = np.concatenate([row_err(gx, Xe), row_err(gy, Ye)])
+    e_gpu = np.concatenate([row_err(gx, Xt), row_err(gy, Yt)])
+    e_ref = np.concatenate([row_err(Xe, Xt), row_err(Ye, Yt)])
+
+    def q(v):
+        return f"max {v.max():.2e} p99.9 {np.quantile(v, 0.999):.2e} median {np.median(v):.2e}"
+
+    print(f"C2 3-iteration fit, all {len(e)} rows: GPU vs fp32 reference {q(e)} (rows above 1e-4: {(e > CHOL_MAX).sum()}); "
+          f"vs the fp64 reference fit: GPU {q(e_gpu)}, fp32 reference {q(e_ref)}")
+    assert np.median(e_gpu) < max(1e-5, 1.5 * np.median(e_ref))
+    assert np.quantile(e_gpu, 0.999) < max(CHOL_MAX, 1.5 * np.quantile(e_ref, 0.999))
+    assert e_gpu.max() < max(CHOL_MAX, 1.5 * e_ref.max())
+    assert np.median(e) < 1e-4 and e.max() < 1e-3
+    loss_g = orc.calculate_loss(Cui, gx, gy, 0.01)
     loss_e = orc.calculate_loss(Cui, Xe, Ye, 0.01)
     print(f"   training loss: GPU factors {loss_g:.7f}, reference factors {loss_e:.7f}")
     assert abs(loss_g - loss_e) < 1e-4 * abs(loss_e)
@@ -147,16 +157,20 @@ def test_c3_warm_cg_half_and_converged_fit(lib, ctx, orc):
     gx, gy = X.download(), Y.download()
     for h in (T, C, X, Y):
         h.close()
-    Xe, Ye = X0.copy(), Y0.copy()
-    oracle.fit(Cui, Xe, Ye, regularization=0.01, iterations=15, use_cg=True, cg_steps=3, kind=orc.name)
-    e15 = np.concatenate([row_err(gx, Xe), row_err(gy, Ye)])
     # How far apart do two CORRECT fp32 runs end up?  The reference itself, restarted from initial factors that differ
     # in the last bit (a 1e-7 relative perturbation), measures the sensitivity of 15 truncated-CG iterations at this
     # size; the GPU must sit inside a small multiple of that, and within CG_CONVERGED_MAX wherever the map is stable.
+    from concurrent.futures import ThreadPoolExecutor
+
     rng = np.random.default_rng(99)
+    Xe, Ye = X0.copy(), Y0.copy()
     Xp = (X0 * (1 + 1e-7 * rng.standard_normal(X0.shape))).astype(np.float32)
     Yp = (Y0 * (1 + 1e-7 * rng.standard_normal(Y0.shape))).astype(np.float32)
-    oracle.fit(Cui, Xp, Yp, regularization=0.01, iterations=15, use_cg=True, cg_steps=3, kind=orc.name)
+    with ThreadPoolExecutor(2) as pool:  # the oracle's OpenMP loops release the GIL: both fits run side by side
+        for j in [pool.submit(oracle.fit, Cui, a, b, regularization=0.01, iterations=15, use_cg=True, cg_steps=3, kind=orc.name)
+                  for a, b in ((Xe, Ye), (Xp, Yp))]:
+            j.result()
+    e15 = np.concatenate([row_err(gx, Xe), row_err(gy, Ye)])
     eself = np.concatenate([row_err(Xp, Xe), row_err(Yp, Ye)])
     print(f"C3 converged (15 iterations), all {len(e15)} rows: GPU vs reference max {e15.max():.2e} p99 {np.quantile(e15, 0.99):.2e} "
           f"median {np.median(e15):.2e}; reference vs itself from 1e-7-perturbed factors: max {eself.max():.2e} "
@@ -165,12 +179,10 @@ def test_c3_warm_cg_half_and_converged_fit(lib, ctx, orc):
     assert np.quantile(e15, 0.99) < max(CG_CONVERGED_MAX, 3 * np.quantile(eself, 0.99))
     assert e15.max() < max(10 * CG_CONVERGED_MAX, 3 * eself.max())
     # the converged objective agrees regardless of where in factor space the two runs sit
-    Ct = Cui.T.tocsr()
     loss_g = orc.calculate_loss(Cui, gx, gy, 0.01)
     loss_e = orc.calculate_loss(Cui, Xe, Ye, 0.01)
     print(f"   training loss: GPU factors {loss_g:.6f}, reference factors {loss_e:.6f}")
     assert abs(loss_g - loss_e) < 2e-3 * abs(loss_e)
-    del Ct
 
 
 # ---------------------------------------------------------------------------------------- C5
