@@ -352,7 +352,7 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
 ALS_API int als_ctx_set_knob(als_ctx *ctx, const char *name, int value) {
   ALS_REQUIRE(ctx && name, "als_ctx_set_knob: NULL argument");
   als_knobs &k = ctx->knobs;
-  if (!strcmp(name, "short_max")) k.short_max = value >= 48 ? 48 : value >= 32 ? 32 : value >= 16 ? 16 : 0;
+  if (!strcmp(name, "short_max")) k.short_max = value >= 48 ? 48 : value <= 0 ? 0 : value / 8 * 8;
   else if (!strcmp(name, "short_serial")) k.short_serial = value != 0;
   else if (!strcmp(name, "whiten_fma")) k.whiten_fma = value != 0;
   else if (!strcmp(name, "gramian_mma")) k.gramian_mma = value != 0;

@@ -290,10 +290,10 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
   }
   // Items of at most `short_max` nonzeros (a suffix of the length-sorted work list) go through the n x n
   // push-through system of cholesky_short.cu when there are enough of them to pay for whitening Y.
-  int short_max = std::min(ctx->knobs.short_max, 16 * (NB - 1));
+  int short_max = std::min(ctx->knobs.short_max, 16 * (NB - 1));  // a multiple of 8; a system of NS unknowns needs NS < F
   int64_t n_main = Cm->n_work;
   if (short_max > 0) {
-    const int64_t begin = Cm->le_begin[short_max > 32 ? 0 : short_max > 16 ? 2 : 4];  // <= 48 / 32 / 16 nonzeros
+    const int64_t begin = Cm->le_begin[(48 - short_max) / 8];  // kShortThresholds: 48, 40, ..., 8
     // worth it when the short rows outweigh whitening all of Y: W = Y P costs ~0.24 ns per row of Y, a short row
     // saves ~4 ns (profiles/r01_short_rows_ab_v4.txt, r01_launches_summary_v2.txt) -> break-even near 1 : 17
     if ((Cm->n_work - begin) * 16 >= Y->rows) n_main = begin;

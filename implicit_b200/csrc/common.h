@@ -53,7 +53,7 @@ constexpr int kChunkNnz = 2048;   // ... into chunks of this many nonzeros (mult
 // Measurement knobs.  Read from the environment ONCE, in als_ctx_create (which reports every knob that is set on
 // stderr); tools flip them afterwards with als_ctx_set_knob.  None changes results beyond fp32 rounding.
 struct als_knobs {
-  int short_max = 48;         // ALS_B200_SHORT_MAX: longest row (nonzeros) of the n x n short-row path: 0 / 16 / 32 / 48
+  int short_max = 48;         // ALS_B200_SHORT_MAX: longest row (nonzeros) of the n x n short-row path: 0, 8, ..., 48
   int short_serial = 0;       // ALS_B200_SHORT_SERIAL: short-row kernels on the compute stream instead of the aux stream
   int whiten_fma = 0;         // ALS_B200_WHITEN_FMA: fp32 FMA tiles for W = Y P, Z = Y G^-1 instead of the tcgen05 apply
   int gramian_mma = 0;        // ALS_B200_GRAMIAN_MMA: legacy mma.sync Gramian
