@@ -320,6 +320,11 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   ALS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ALS_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
   ALS_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; ++i) {
+    ALS_CUDA(cudaStreamCreateWithFlags(&ctx->class_stream[i], cudaStreamNonBlocking));
+    ALS_CUDA(cudaEventCreateWithFlags(&ctx->class_join[i], cudaEventDisableTiming));
+  }
+  ALS_CUDA(cudaEventCreateWithFlags(&ctx->class_fork, cudaEventDisableTiming));
   ALS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   ALS_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   ALS_CUDA(cudaEventCreateWithFlags(&ctx->sched_ev, cudaEventDisableTiming));
@@ -400,6 +405,11 @@ ALS_API int als_ctx_destroy(als_ctx *ctx) {
   }
   if (ctx->sched_pinned) cudaFreeHost(ctx->sched_pinned);
   cudaEventDestroy(ctx->sched_ev);
+  for (int i = 0; i < 5; ++i) {
+    if (ctx->class_stream[i]) cudaStreamDestroy(ctx->class_stream[i]);
+    if (ctx->class_join[i]) cudaEventDestroy(ctx->class_join[i]);
+  }
+  if (ctx->class_fork) cudaEventDestroy(ctx->class_fork);
   {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);

@@ -25,8 +25,11 @@ namespace {
 
 // ---- kernel ------------------------------------------------------------------------------------
 // pass 0: whole rows and chunks of giant rows;  pass 1: finish giant rows from their chunk slots.
+#ifndef ALS_LONG_MIN_BLOCKS
+#define ALS_LONG_MIN_BLOCKS 11  // one-warp CTAs per SM the register allocation aims at (variants: tools/build_variant.sh)
+#endif
 template <int NB>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 11)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, ALS_LONG_MIN_BLOCKS)
 cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
                      float *__restrict__ X, int64_t row_offset, const float *__restrict__ Greg,
                      const WorkItem *__restrict__ work, int n_work, const int32_t *n_work_dev, int32_t *counter,

@@ -659,18 +659,35 @@ int run_short_classes(als_ctx *ctx, const als_csr *Cm, als_factors *X, int64_t b
     return ALS_E_INVALID;
   }
   (void)max_len;
+  // One stream per size class (forked from `stream`, joined back into it): the classes are persistent kernels of very
+  // different lengths, and on one stream each would wait for the previous one's tail -- a cost that does not shrink
+  // with the row shard of a multi-GPU run.  Longest class first.
+  const bool fan = ctx->class_stream[0] != nullptr && !ctx->knobs.short_serial;
+  if (fan) ALS_CUDA(cudaEventRecord(ctx->class_fork, stream));
   int rc = ALS_OK;
-  // longest first: the classes with the most work per row start (and spread over the SMs) before the cheap ones
+  int used = 0;
+  auto on = [&](int slot) -> cudaStream_t {
+    if (!fan || slot == 0) return stream;
+    cudaStreamWaitEvent(ctx->class_stream[slot - 1], ctx->class_fork, 0);
+    used |= 1 << slot;
+    return ctx->class_stream[slot - 1];
+  };
   if constexpr (NB >= 4) {
-    if ((rc = run_short<NB, 48>(ctx, Cm, X, lb[0], lb[1], 0, stream)) != ALS_OK) return rc;
-    if ((rc = run_short<NB, 40>(ctx, Cm, X, lb[1], lb[2], 1, stream)) != ALS_OK) return rc;
+    if (lb[1] > lb[0] && (rc = run_short<NB, 48>(ctx, Cm, X, lb[0], lb[1], 0, on(0))) != ALS_OK) return rc;
+    if (lb[2] > lb[1] && (rc = run_short<NB, 40>(ctx, Cm, X, lb[1], lb[2], 1, on(1))) != ALS_OK) return rc;
   }
   if constexpr (NB >= 3) {
-    if ((rc = run_short<NB, 32>(ctx, Cm, X, lb[2], lb[3], 2, stream)) != ALS_OK) return rc;
-    if ((rc = run_short<NB, 24>(ctx, Cm, X, lb[3], lb[4], 3, stream)) != ALS_OK) return rc;
+    if (lb[3] > lb[2] && (rc = run_short<NB, 32>(ctx, Cm, X, lb[2], lb[3], 2, on(2))) != ALS_OK) return rc;
+    if (lb[4] > lb[3] && (rc = run_short<NB, 24>(ctx, Cm, X, lb[3], lb[4], 3, on(3))) != ALS_OK) return rc;
   }
-  if ((rc = run_short<NB, 16>(ctx, Cm, X, lb[4], lb[5], 4, stream)) != ALS_OK) return rc;
-  return run_short<NB, 8>(ctx, Cm, X, lb[5], Cm->n_work, 5, stream);
+  if (lb[5] > lb[4] && (rc = run_short<NB, 16>(ctx, Cm, X, lb[4], lb[5], 4, on(4))) != ALS_OK) return rc;
+  if (Cm->n_work > lb[5] && (rc = run_short<NB, 8>(ctx, Cm, X, lb[5], Cm->n_work, 5, on(5))) != ALS_OK) return rc;
+  for (int slot = 1; slot < 6; ++slot)
+    if (used & (1 << slot)) {
+      ALS_CUDA(cudaEventRecord(ctx->class_join[slot - 1], ctx->class_stream[slot - 1]));
+      ALS_CUDA(cudaStreamWaitEvent(stream, ctx->class_join[slot - 1], 0));
+    }
+  return ALS_OK;
 }
 
 }  // namespace

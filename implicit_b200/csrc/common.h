@@ -73,6 +73,8 @@ struct als_ctx {
   cudaStream_t copy = nullptr;     // H2D / D2H staging
   cudaStream_t aux = nullptr;      // short-row kernels of a Cholesky half, concurrent with the full-size kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t class_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // short-row size classes 2..6 (the first stays on aux)
+  cudaEvent_t class_fork = nullptr, class_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   // Gramian state: G (f_pad x f_pad, without lambda) and Greg (G + lambda I, identity on padded dims)
