@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink rows/cols/nnz together (debugging only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
@@ -654,6 +654,67 @@ def run_topk(args):
         "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}))
 
 
+# --------------------------------------------------------------------------------------- the reference's own CUDA kernel
+def run_reference_gpu(args):
+    """The reference's CUDA ALS solver (implicit/gpu/als.cu: cuBLAS Gramian + least_squares_cg_kernel), compiled
+    unchanged into oracle/_ref/libref_gpu_als.so (oracle/build_ref_gpu.py), driven like implicit/gpu/als.py:159-165 on the
+    same workload and initial factors, on GPU 0.  CG only (the reference has no GPU Cholesky); for the Cholesky
+    configuration C2 this is its answer to the same problem.  Reports the SAME metric, plus parity with our CG path."""
+    import ctypes
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from implicit_b200 import _lib, synthetic
+
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_gpu_als.so")
+    if not os.path.exists(path):
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/libref_gpu_als.so was not built (oracle/build_ref_gpu.py needs /root/reference)"}))
+        return
+    lib = ctypes.CDLL(path)
+    Cui, X0, Y0, cfg = synthetic.config(args.config, scale=args.scale)
+    users, items, f = cfg["users"], cfg["items"], cfg["factors"]
+    Ciu = Cui.T.tocsr()
+    iters = args.warmup + args.steps
+    X, Y = X0.copy(), Y0.copy()
+    ms = np.zeros(iters, dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    ui = [np.ascontiguousarray(Cui.indptr, np.int32), np.ascontiguousarray(Cui.indices, np.int32), np.ascontiguousarray(Cui.data, np.float32)]
+    iu = [np.ascontiguousarray(Ciu.indptr, np.int32), np.ascontiguousarray(Ciu.indices, np.int32), np.ascontiguousarray(Ciu.data, np.float32)]
+    rc = lib.ref_gpu_als_cg_fit(users, items, f, p(ui[0]), p(ui[1]), p(ui[2]), int(Cui.nnz), p(iu[0]), p(iu[1]), p(iu[2]), p(X), p(Y),
+                                ctypes.c_float(0.01), 3, iters, p(ms))
+    if rc != 0:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": f"harness returned {rc}"}))
+        return
+    timed = ms[args.warmup:]
+    value = (users + items) * len(timed) / (float(timed.sum()) * 1e-3)
+    # parity of OUR CG path with the reference's CUDA kernel after the same number of iterations (both fp32, CG(3))
+    ctx = _lib.Context(0)
+    C = _lib.DeviceCSR.upload(ctx, Cui)
+    T = C.transpose()
+    dX, dY = _lib.DeviceFactors.from_host(ctx, X0), _lib.DeviceFactors.from_host(ctx, Y0)
+    ctx.timer_start()
+    for _ in range(iters):
+        _lib.least_squares_cg(ctx, C, dX, dY, 0.01, 3)
+        _lib.least_squares_cg(ctx, T, dY, dX, 0.01, 3)
+    ours_ms = ctx.timer_stop() / iters
+    gx = dX.download()
+    den = np.linalg.norm(X.astype(np.float64), axis=1)
+    err = np.linalg.norm(gx.astype(np.float64) - X, axis=1) / np.maximum(den, 0.01 * np.median(den))
+    print(json.dumps({
+        "impl": "reference-gpu", "metric": metric_name(dict(cfg, use_cg=True)), "value": value, "unit": UNIT, "n_gpus": 1,
+        "steps": int(len(timed)), "warmup": args.warmup, "ms_per_step": float(timed.mean()), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(dict(cfg, use_cg=True), args, 1),
+                       note="the reference's GPU path is CG-only: implicit/gpu/als.cu least_squares_cg_kernel + cublasSgemm Gramian, compiled for sm_100a"),
+        "ms_per_iteration": [round(float(x), 3) for x in ms],
+        "ours_cg_same_workload": {"ms_per_step": ours_ms, "value": (users + items) / (ours_ms * 1e-3),
+                                  "speedup_over_reference_gpu": float(timed.mean()) / ours_ms,
+                                  "row_err_vs_reference_gpu": {"median": float(np.median(err)), "p99": float(np.quantile(err, 0.99)),
+                                                               "max": float(err.max()),
+                                                               "note": f"user factors after {iters} CG(3) iterations from the same start"}},
+        "gpu_launches": 4 * iters}))
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -666,7 +727,9 @@ def main():
                        MASTER_PORT=str(port))
             procs.append(subprocess.Popen([sys.executable] + sys.argv, env=env))
         sys.exit(max(p.wait() for p in procs))
-    if args.config == "C5":
+    if args.impl == "reference-gpu":
+        run_reference_gpu(args)
+    elif args.config == "C5":
         (run_topk_reference if args.impl == "reference" else run_topk)(args)
     elif args.impl == "reference":
         run_reference(args)
