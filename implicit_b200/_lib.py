@@ -452,7 +452,7 @@ def solver_status(ctx):
         raise ValueError("cholesky failed on row %i. Try increasing the regularization parameter." % bad.value)
     check(rc)
     if anyf.value:
-        raise AlsError("another rank failed in this iteration (see its error message)")
+        raise AlsError(ALS_E_NOT_POSDEF, "another rank failed in this iteration (see its error message)")
 
 
 def half_pregram(ctx, Cui, X, Y, regularization, use_cg, cg_steps=3):

@@ -284,7 +284,7 @@ class AlternatingLeastSquares:
         if err is not None:
             raise err
         if failed:
-            raise _lib.AlsError("another rank failed in this half-iteration (see its error message)")
+            raise _lib.AlsError(_lib.ALS_E_NOT_POSDEF, "another rank failed in this half-iteration (see its error message)")
 
     def _loss(self, C, X, Y, users, items, nnz):
         ctx = self.ctx

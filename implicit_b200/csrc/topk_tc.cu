@@ -7,11 +7,14 @@
 //   pre-pass   both factor matrices are split ONCE per call into fp16 hi / lo halves (x 2^e, e from the matrix's
 //              absolute maximum, so the halves carry 22 bits): scores = (Qh + Ql)(Ih + Il)^T ~ Ql Ih^T + Qh Il^T + Qh Ih^T,
 //              fp32-faithful like the 3xTF32 split of topk.cu at half the tensor work and half the operand bytes;
-//   CTA        128 query rows (hi and lo tiles resident in shared memory, K-major, 128B swizzle) sweep ALL items:
+//   CTA        2 x 128 query rows (hi and lo tiles resident in shared memory, K-major, 128B swizzle) sweep ALL items;
+//              every landed item tile is multiplied with BOTH query tiles (half the L2 -> SM operand traffic of one
+//              query tile per CTA: the sweep streams 256 B per item and CTA):
 //              warp 0   TMA producer: 256-item hi + lo boxes into a 2-stage ring (mbarrier complete_tx);
-//              warp 1   one lane issues 12 tcgen05.mma.kind::f16 (M = 128, N = 256, K = 16) per item tile into one
-//                       of two 128 x 256 fp32 accumulators in TMEM (all 512 columns), tcgen05.commit when done;
-//              warps 2-5 one THREAD per query row: tcgen05.ld of its 256 scores, a running threshold (the k-th best
+//              warp 1   one lane issues, per item tile and query tile, 12 tcgen05.mma.kind::f16 (M = 128, N = 256,
+//                       K = 16) into that query tile's 128 x 256 fp32 accumulator in TMEM (2 x 256 = all 512
+//                       columns), tcgen05.commit per accumulator: tile A is selected from while tile B is multiplied;
+//              warps 2-9 (four per query tile) one THREAD per query row: tcgen05.ld of its 256 scores, a running threshold (the k-th best
 //                       so far) rejects almost everything with one max + compare per 32 scores; survivors are checked
 //                       against the row's liked list (a cursor: both advance in item order) and the global filter
 //                       mask, then inserted into a sorted k-list held in REGISTERS with exactly the reference's
@@ -31,17 +34,18 @@ namespace als {
 namespace {
 
 constexpr int kTkF = 64;
-constexpr int kTkQ = 128;                // query rows per CTA
+constexpr int kTkQ = 128;                // query rows per MMA tile
+constexpr int kTkG = 2;                  // query tiles per CTA: both are multiplied with every landed item tile
 constexpr int kTkI = 256;                // items per tile
-constexpr int kTkThreads = 192;
+constexpr int kTkThreads = 64 + 128 * kTkG;
 constexpr int kQBytes = kTkQ * 128;      // one 128-row x 64-half tile
 constexpr int kIBytes = kTkI * 128;      // one 256-row x 64-half tile
-constexpr int kTkOffQ = 0;               // Qh | Ql
-constexpr int kTkOffI = 2 * kQBytes;     // 2 stages x (Ih | Il)
-constexpr int kTkOffCand = kTkOffI + 4 * kIBytes;  // [32][128] floats: a chunk of scores per selecting thread, column major
-constexpr int kTkOffBar = kTkOffCand + 32 * 128 * 4;
+constexpr int kTkOffQ = 0;               // per query tile: Qh | Ql
+constexpr int kTkOffI = kTkG * 2 * kQBytes;        // 2 stages x (Ih | Il)
+constexpr int kTkOffCand = kTkOffI + 4 * kIBytes;  // [32][256] floats: a chunk of scores per selecting thread, column major
+constexpr int kTkOffBar = kTkOffCand + 32 * 128 * kTkG * 4;
 constexpr int kTkSmem = kTkOffBar + 128 + 1024;
-enum { kTQFull = 0, kTFull0, kTFull1, kTMma0, kTMma1, kTFree0, kTFree1, kTNumBars };
+enum { kTQFull = 0, kTFull0, kTFull1, kTMma0, kTMma1, kTAccFull0, kTAccFull1, kTAccFree0, kTAccFree1, kTNumBars };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -91,20 +95,25 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+// tcgen05.ld is asynchronous: the registers are valid only after tcgen05.wait::ld.  The wait below takes the registers as
+// read-write operands, so every use of the values depends on it and the compiler cannot hoist one above the wait; this
+// lets the NEXT chunk's load be in flight while the current chunk is scanned.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 // ---- pre-pass -------------------------------------------------------------------------------------
@@ -181,7 +190,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gbase + kTkOffBar + 8 * kTNumBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_items + kTkI - 1) / kTkI;
-  const int q0 = (int)blockIdx.x * kTkQ;
+  const int q0 = (int)blockIdx.x * kTkQ * kTkG;
 
   if (threadIdx.x == 0) {
     mbar_init(bar(kTQFull), 1);
@@ -189,8 +198,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     mbar_init(bar(kTFull1), 1);
     mbar_init(bar(kTMma0), 1);
     mbar_init(bar(kTMma1), 1);
-    mbar_init(bar(kTFree0), 128);
-    mbar_init(bar(kTFree1), 128);
+    mbar_init(bar(kTAccFull0), 1);
+    mbar_init(bar(kTAccFull1), 1);
+    mbar_init(bar(kTAccFree0), 128);
+    mbar_init(bar(kTAccFree1), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -206,9 +217,12 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar(kTQFull), 2 * kQBytes);
-      tma_load_2d(base + kTkOffQ, &map_qh, bar(kTQFull), 0, q0);
-      tma_load_2d(base + kTkOffQ + kQBytes, &map_ql, bar(kTQFull), 0, q0);
+      mbar_expect_tx(bar(kTQFull), kTkG * 2 * kQBytes);
+#pragma unroll
+      for (int gq = 0; gq < kTkG; ++gq) {
+        tma_load_2d(base + kTkOffQ + gq * 2 * kQBytes, &map_qh, bar(kTQFull), 0, q0 + gq * kTkQ);
+        tma_load_2d(base + kTkOffQ + gq * 2 * kQBytes + kQBytes, &map_ql, bar(kTQFull), 0, q0 + gq * kTkQ);
+      }
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t & 1;
         if (t >= 2) mbar_wait(bar(kTMma0 + s), (uint32_t)(((t >> 1) - 1) & 1));  // the MMAs of tile t - 2 have read the stage
@@ -220,34 +234,40 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       mbar_wait(bar(kTQFull), 0);
-      const uint32_t qh = base + kTkOffQ, ql = qh + kQBytes;
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t & 1;
         mbar_wait(bar(kTFull0 + s), (uint32_t)((t >> 1) & 1));
-        if (t >= 2) mbar_wait(bar(kTFree0 + s), (uint32_t)(((t >> 1) - 1) & 1));  // accumulator s has been selected from
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(s * kTkI);
         const uint32_t ih = base + kTkOffI + s * 2 * kIBytes, il = ih + kIBytes;
-        uint32_t acc = 0;
 #pragma unroll
-        for (int term = 0; term < 3; ++term) {  // lo * hi, hi * lo, hi * hi (small terms first)
-          const uint32_t a0 = term == 0 ? ql : qh;
-          const uint32_t b0 = term == 1 ? il : ih;
+        for (int gq = 0; gq < kTkG; ++gq) {
+          if (t >= 1) mbar_wait(bar(kTAccFree0 + gq), (uint32_t)((t - 1) & 1));  // tile t - 1 has been selected from
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d = tmem_base + (uint32_t)(gq * kTkI);
+          const uint32_t qh = base + kTkOffQ + gq * 2 * kQBytes, ql = qh + kQBytes;
+          uint32_t acc = 0;
 #pragma unroll
-          for (int ks = 0; ks < kTkF / 16; ++ks) {
-            umma_f16(d, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), acc);
-            acc = 1;
+          for (int term = 0; term < 3; ++term) {  // lo * hi, hi * lo, hi * hi (small terms first)
+            const uint32_t a0 = term == 0 ? ql : qh;
+            const uint32_t b0 = term == 1 ? il : ih;
+#pragma unroll
+            for (int ks = 0; ks < kTkF / 16; ++ks) {
+              umma_f16(d, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), acc);
+              acc = 1;
+            }
           }
+          umma_commit(bar(kTAccFull0 + gq));
         }
-        umma_commit(bar(kTMma0 + s));
+        umma_commit(bar(kTMma0 + s));  // both query tiles have read the stage
       }
     }
   } else {
     // ===== selection: one thread per query row =====
-    const int quarter = warp & 3;
-    const int st = threadIdx.x - 64;  // 0..127
+    const int quarter = warp & 3;      // the TMEM lanes this warp may read
+    const int gq = (warp - 2) >> 2;    // which query tile (accumulator) this warp selects from
+    const int st = threadIdx.x - 64;   // 0 .. 128 kTkG - 1
+    constexpr int kCandLd = 128 * kTkG;
     float *cand = reinterpret_cast<float *>(gbase + kTkOffCand);
-    const int q = q0 + 32 * quarter + lane;
+    const int q = q0 + gq * kTkQ + 32 * quarter + lane;
     const bool live = q < n_query;
     float ls[KMAX];
     int lc[KMAX];
@@ -287,32 +307,43 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
       for (int j = 0; j < KMAX; ++j)
         if (j == k - 1) thr = ls[j];
     };
-    for (int t = 0; t < n_tiles; ++t) {
-      const int s = t & 1;
-      mbar_wait(bar(kTMma0 + s), (uint32_t)((t >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int c = 0; c < kTkI / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(s * kTkI + 32 * c), v);
-        float m = v[0];
+    // one 32-column chunk of the accumulator row: skip it unless something beats the k-th best so far
+    auto scan = [&](const uint32_t (&r)[32], int id0) {
+      float m[8];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-        if (live && m > thr) {
-          // rare after the first tiles: park the chunk in shared memory (one column per thread, conflict free) and walk
-          // it in item order with a rolled loop, so the k-list code exists once and its arrays stay in registers
+      for (int j = 0; j < 8; ++j) m[j] = fmax3(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]));
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cand[j * 128 + st] = v[j];
-          const int id0 = t * kTkI + 32 * c;
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __uint_as_float(r[4 * j + 3]));
+      const float mm = fmaxf(fmax3(m[0], m[1], m[2]), fmaxf(fmax3(m[3], m[4], m[5]), fmaxf(m[6], m[7])));
+      if (live && mm > thr) {
+        // rare after the first tiles: park the chunk in shared memory (one column per thread, conflict free) and walk
+        // it in item order with a rolled loop, so the k-list code exists once and its arrays stay in registers
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cand[j * kCandLd + st] = __uint_as_float(r[j]);
 #pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
-            const float sc = cand[j * 128 + st];
-            if (sc > thr) consider(sc, id0 + j);
-          }
+        for (int j = 0; j < 32; ++j) {
+          const float sc = cand[j * kCandLd + st];
+          if (sc > thr) consider(sc, id0 + j);
         }
       }
+    };
+    const uint32_t trow = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(gq * kTkI);
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(bar(kTAccFull0 + gq), (uint32_t)(t & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t ra[32], rb[32];
+      tmem_ld32_issue(trow, ra);
+#pragma unroll 1
+      for (int c = 0; c < kTkI / 32; c += 2) {
+        tmem_ld32_wait(ra);
+        tmem_ld32_issue(trow + 32 * (c + 1), rb);
+        scan(ra, t * kTkI + 32 * c);
+        tmem_ld32_wait(rb);
+        if (c + 2 < kTkI / 32) tmem_ld32_issue(trow + 32 * (c + 2), ra);
+        scan(rb, t * kTkI + 32 * (c + 1));
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(bar(kTFree0 + s));
+      mbar_arrive(bar(kTAccFree0 + gq));
     }
     if (live) {
       // scores leave the scaled domain: exact multiplications by powers of two
@@ -373,7 +404,7 @@ int64_t topk_tc_scratch_bytes(int64_t n_query, int64_t n_items) {
 }
 
 bool topk_tc_eligible(int ld, int64_t n_query, int64_t n_items, int k, bool has_norms) {
-  return ld == kTkF && k >= 1 && k <= 16 && !has_norms && n_query >= 1024 && n_items >= kTkI && n_query >= kTkQ;
+  return ld == kTkF && k >= 1 && k <= 16 && !has_norms && n_query >= 1024 && n_items >= kTkI;
 }
 
 // out_ids / out_scores: device [n_query][k], zero-initialised by the caller; query_rows: device indices or nullptr
@@ -401,7 +432,7 @@ int launch_topk_tc(als_ctx *ctx, const float *items, int64_t n_items, const floa
   if ((rc = make_half_map(&mil, il, n_items, kTkI)) != ALS_OK) return rc;
   auto kern = topk_tc_kernel<16>;
   ALS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTkSmem));
-  const int grid = (int)ceil_div(n_query, kTkQ);
+  const int grid = (int)ceil_div(n_query, kTkQ * kTkG);
   {
     ProfScope prof(ctx, kProfTopk);
     kern<<<grid, kTkThreads, kTkSmem, ctx->stream>>>(mqh, mql, mih, mil, (int)n_items, (int)n_query, k, absmax, absmax + 1, mask,

@@ -61,6 +61,17 @@ for use_cg in (False, True):
     else:
         _lib.least_squares(ctx, C, Xs, Ys, 0.01)
     single = Xs.download()
+    # the sharded half differs from this one only by the summation order of the Gramian: calibrate the gate with the
+    # same half from item factors perturbed in the last bit (3 unconverged CG steps amplify that on ill-conditioned rows)
+    Yq = _lib.DeviceFactors.from_host(ctx, (Yw * (1 + 1e-7 * np.random.default_rng(7).standard_normal(Yw.shape))).astype(np.float32))
+    Xq = _lib.DeviceFactors.from_host(ctx, Xw)
+    if use_cg:
+        _lib.least_squares_cg(ctx, C, Xq, Yq, 0.01, 3)
+    else:
+        _lib.least_squares(ctx, C, Xq, Yq, 0.01)
+    sens = row_err(Xq.download(), single)
+    Xq.close()
+    Yq.close()
     for p2p in (True, False):
         Xd, Yd = _lib.DeviceFactors.from_host(ctx, Xw), _lib.DeviceFactors.from_host(ctx, Yw)
         isplit = nnz_balanced_splits(Cui.T.tocsr().indptr, world, 60)
@@ -78,8 +89,8 @@ for use_cg in (False, True):
             ctx.allgather_rows(Xd, usplit)
         e = row_err(Xd.download(), single)
         say(f"one {'cg' if use_cg else 'cholesky'} half, {'peer stores' if p2p else 'all-gather'}: row err max {e.max():.2e} "
-            f"median {np.median(e):.2e}")
-        ok &= bool(e.max() < 2e-5 and np.median(e) < 2e-6)
+            f"median {np.median(e):.2e} (single GPU, item factors perturbed by 1e-7: max {sens.max():.2e} median {np.median(sens):.2e})")
+        ok &= bool(e.max() < max(2e-5, 3 * sens.max()) and np.median(e) < max(2e-6, 3 * np.median(sens)))
         Xd.close()
         Yd.close()
     Xs.close()
