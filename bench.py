@@ -489,7 +489,8 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------- C5: recommend
-C5 = dict(users=1_000_000, items=1_000_000, factors=64, k=10, liked_per_user=20, batch=65_536, seed=5)
+# batch: two full waves of the top-k kernel's 256-query CTAs on 148 SMs (the 1M-user sweep is 13.2 such batches)
+C5 = dict(users=1_000_000, items=1_000_000, factors=64, k=10, liked_per_user=20, batch=2 * 148 * 256, seed=5)
 
 
 def c5_inputs(scale):

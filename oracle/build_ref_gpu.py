@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
             fh.write(RMM_STUB)
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                "-ccbin", "/usr/bin/g++", "-I", tmp, "-I", REFERENCE, os.path.join(HERE, "ref_gpu", "harness.cu"), "-o", OUT,
-               "-lcublas", "-lcudart"]
+               "-lcublas", "-lcudart", "-Xlinker", "--no-undefined"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

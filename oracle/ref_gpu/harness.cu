@@ -17,6 +17,16 @@ CSRMatrix::CSRMatrix(int rows, int cols, int nonzeros, const int *indptr_, const
     : indptr(const_cast<int *>(indptr_)), indices(const_cast<int *>(indices_)), data(const_cast<float *>(data_)), rows(rows),
       cols(cols), nonzeros(nonzeros) {}
 CSRMatrix::~CSRMatrix() {}
+// LeastSquaresSolver::calculate_loss (als.cu:253-281, not called by this harness) refers to these two members of
+// implicit/gpu/matrix.cu; plain cudaMalloc stand-ins so that the shared object has no undefined symbol
+Matrix::Matrix(size_t rows_, size_t cols_, void *host, bool allocate, size_t itemsize_)
+    : rows(rows_), cols(cols_), data(host), itemsize(itemsize_) {
+  if (allocate) {
+    CHECK_CUDA(cudaMalloc(&data, rows * cols * itemsize));  // never freed: test infrastructure
+    if (host) CHECK_CUDA(cudaMemcpy(data, host, rows * cols * itemsize, cudaMemcpyHostToDevice));
+  }
+}
+void Matrix::to_host(void *output) const { CHECK_CUDA(cudaMemcpy(output, data, rows * cols * itemsize, cudaMemcpyDeviceToHost)); }
 // implicit/gpu/als.cu declares the destructor in als.h and defines it near the end of the file
 }  // namespace gpu
 }  // namespace implicit
