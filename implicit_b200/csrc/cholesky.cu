@@ -195,15 +195,19 @@ cholesky_half_kernel(const int32_t *__restrict__ indices, const float *__restric
   cp_async_wait<0>();
 }
 
-// max over [begin, end) of | |c| - 1 | (bits; NaN / inf left out) -- the weight range of a CSR, cached in the handle
+// out[0] = max over [begin, end) of | |c| - 1 | (bits; NaN / inf left out), out[1] = 1 when some weight |c| - 1 is negative
+// -- the weight range of a CSR, cached in the handle
 __global__ void __launch_bounds__(256) csr_wmax_kernel(const int32_t *__restrict__ indptr, int64_t rows,
                                                        const float *__restrict__ data, unsigned *out) {
   const int64_t begin = indptr[0], end = indptr[rows];
-  unsigned m = 0;
+  unsigned m = 0, neg = 0;
   for (int64_t e = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < end; e += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned b = __float_as_uint(fabsf(fabsf(__ldg(data + e)) - 1.f));
+    const float w = fabsf(__ldg(data + e)) - 1.f;
+    const unsigned b = __float_as_uint(fabsf(w));
     if (b < 0x7f800000u) m = max(m, b);
+    if (w < 0.f) neg = 1;
   }
+  if (neg) out[1] = 1;  // benign race: every writer stores the same value
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
@@ -281,15 +285,24 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
   ctx->launches++;
   als_csr *Cmut = const_cast<als_csr *>(Cm);
   if (!Cmut->wmax_dev) {
-    int arc = dev_alloc(ctx, (void **)&Cmut->wmax_dev, sizeof(unsigned));  // stream-ordered pool: no cudaMalloc per fit
+    int arc = dev_alloc(ctx, (void **)&Cmut->wmax_dev, 2 * sizeof(unsigned));  // stream-ordered pool: no cudaMalloc per fit
     if (arc != ALS_OK) return arc;
   }
   if (!Cmut->wmax_valid) {
-    ALS_CUDA(cudaMemsetAsync(Cmut->wmax_dev, 0, sizeof(unsigned), ctx->stream));
+    ALS_CUDA(cudaMemsetAsync(Cmut->wmax_dev, 0, 2 * sizeof(unsigned), ctx->stream));
     csr_wmax_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(Cm->indptr, Cm->rows, Cm->data, Cmut->wmax_dev);
     ALS_CUDA(cudaGetLastError());
     ctx->launches++;
     Cmut->wmax_valid = true;
+    Cmut->neg_w_known = false;
+  }
+  if (NB == 4 && !Cmut->neg_w_known && !ctx->knobs.long_legacy) {
+    // which long-row kernel: one 4-byte read-back per CSR (not per half), cached like the weight range
+    unsigned flag = 0;
+    ALS_CUDA(cudaMemcpyAsync(&flag, Cmut->wmax_dev + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+    Cmut->has_neg_w = flag != 0;
+    Cmut->neg_w_known = true;
   }
   // Items of at most `short_max` nonzeros (a suffix of the length-sorted work list) go through the n x n
   // push-through system of cholesky_short.cu when there are enough of them to pay for whitening Y.
@@ -318,7 +331,19 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
       int rc = short_rows_prepare(ctx, Y, side);
       if (rc != ALS_OK) return rc;
     }
-    if (n_main) {
+    if (n_main && NB == 4 && cholesky_tc_eligible(ctx, Cm, Y->ld)) {
+      // whole rows: normal equations on the tcgen05 tensor cores; chunks of giant rows: the mma.sync kernel
+      int rc = launch_cholesky_tc(ctx, Cm, X, Y, n_main, ctx->stream);
+      if (rc != ALS_OK) return rc;
+      if (Cm->n_slots) {
+        const int grid = (int)std::min<int64_t>(ceil_div(Cm->n_slots, kWarpsPerCta), max_grid);
+        kern<<<grid, 32 * kWarpsPerCta, smem, side>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg, Cm->chunks,
+                                                       (int)Cm->n_slots, nullptr, ctx->counters + kCtrChunks, slots, ctx->bad_row,
+                                                       0, dbg, X->peers_dev, X->n_peers, Cm->wmax_dev, yabsmax);
+        ALS_CUDA(cudaGetLastError());
+        ctx->launches++;
+      }
+    } else if (n_main) {
       const int grid = (int)std::min<int64_t>(ceil_div(n_main, kWarpsPerCta), max_grid);
       kern<<<grid, 32 * kWarpsPerCta, smem, ctx->stream>>>(Cm->indices, Cm->data, Y->d, X->d, Cm->row_offset, ctx->Greg,
                                                             Cm->work, (int)n_main, nullptr, ctx->counters + kCtrMain,

@@ -59,6 +59,7 @@ struct als_knobs {
   int gramian_mma = 0;        // ALS_B200_GRAMIAN_MMA: legacy mma.sync Gramian
   int topk_legacy = 0;        // ALS_B200_TOPK_LEGACY: mma.sync top-k kernel for every call (no tcgen05 path)
   int gramian_fma = 0;        // ALS_B200_GRAMIAN_FMA: fp32 FMA Gramian instead of the tcgen05 one (64 padded factors)
+  int long_legacy = 0;        // ALS_B200_LONG_LEGACY: mma.sync kernel for the long rows of a Cholesky half (no tcgen05 path)
   int cg_nv = 2;              // ALS_B200_CG_NV: float4 words per lane of the CG kernel (1 / 2 / 4)
 };
 
@@ -150,8 +151,9 @@ struct als_csr {
   // work is sorted by length, so the items of at most 48 / 40 / ... / 8 / 0 nonzeros are suffixes: first index of each
   int64_t le_begin[7] = {0, 0, 0, 0, 0, 0, 0};
   int64_t max_row_nnz = 0;     // longest row (known once the schedule is built)
-  unsigned *wmax_dev = nullptr;  // device scalar: bits of max | |c| - 1 | over the values (cholesky.cu), computed lazily
+  unsigned *wmax_dev = nullptr;  // device: [0] bits of max | |c| - 1 | over the values, [1] != 0 when some |c| < 1 (cholesky.cu), computed lazily
   bool wmax_valid = false;
+  bool neg_w_known = false, has_neg_w = false;  // host copy of wmax_dev[1]: weights |c| - 1 < 0 exist (then no tcgen05 long-row path)
   bool sched_pending = false;  // transposed on the device: the schedule is built at first use (ensure_schedule)
   als::WorkItem *finish = nullptr;  // finish pass: one per giant row (row, first slot, #slots)
   int64_t n_finish = 0;
@@ -174,6 +176,7 @@ enum { kProfGramian = 0, kProfCholesky = 1, kProfCholFinish = 2, kProfCg = 3, kP
 // slots of als_ctx::counters
 enum {
   kCtrMain = 0, kCtrFinish = 1, kCtrDeferredCount = 2, kCtrDeferredWork = 3, kCtrWhitenOk = 4, kCtrHasNan = 5, kCtrYAbsMax = 6,
+  kCtrChunks = 7,
   kCtrShort = 8 /* +0..5: one per short-row size class */
 };
 // size classes of the short-row path: als_csr::le_begin[i] is the first work item of at most kShortThresholds[i] nonzeros
@@ -202,6 +205,9 @@ int comm_allreduce_gramian(als_ctx *ctx, int n_floats);                   // sum
 int launch_regularize(als_ctx *ctx, int f, int ld, float lambda);         // ctx->G -> ctx->Greg
 int launch_cholesky(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y);
 int launch_cholesky_wide(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y);
+// long rows on the tcgen05 tensor cores (cholesky_tc.cu): 64 padded factors, no weights |c| - 1 < 0
+bool cholesky_tc_eligible(const als_ctx *ctx, const als_csr *C, int ld);
+int launch_cholesky_tc(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors *Y, int64_t n_items, cudaStream_t stream);
 // short-row path (cholesky_short.cu).  prepare: P and W from ctx->Greg and Y.  launch: items [begin, n_work) of
 // C->work, all of at most `max_len` nonzeros; whatever it cannot take lands in ctx->deferred / counters[kCtrDeferredCount].
 int short_rows_prepare(als_ctx *ctx, const als_factors *Y, cudaStream_t stream);
