@@ -5,22 +5,27 @@
 //   A_u = (Y^T Y + lambda I) + sum_k w_k y_k y_k^T  with  w_k = |c_k| - 1 >= 0   is   G + Z^T Z,  Z = [sqrt(w_k) y_k]:
 //   a GEMM whose operand rows are exactly what the gather produces.  One persistent CTA per SM, warp specialised:
 //
-//   producers (3 warps)  take 32 nonzeros of the current row per ring stage: 16 coalesced 16-byte loads per lane of the
-//                        gathered factor rows, scale by sigma sqrt(w), split into fp16 hi + lo (both rounded to
-//                        nearest) and store the two 32 x 64 tiles MN-major with the 128-byte swizzle -- a nonzero is
-//                        one 128-byte row of the tile.  b_u = sum c_k y_k rides along in fp32 (one partial per producer,
-//                        summed in a fixed order);
-//   MMA warp (one lane)  per 16 nonzeros three tcgen05.mma.kind::f16 (M = N = 64, K = 16): lo^T hi + hi^T lo + hi^T hi
-//                        into one of eight 64-column fp32 accumulators in TMEM, tcgen05.commit frees the stage / hands
-//                        the row over;
+//   producers (7 warps)  take 32 nonzeros of the current row per ring stage: coalesced 16-byte loads of the gathered
+//                        factor rows, scale by sigma sqrt(w), split into fp16 hi + lo (both rounded to nearest) and
+//                        store the two 32 x 64 tiles MN-major with the 128-byte swizzle -- a nonzero is one 128-byte
+//                        row of the tile.  b_u = sum c_k y_k rides along in fp32 (one partial per producer, summed in
+//                        a fixed order);
+//   MMA warp (one lane)  per 16 nonzeros two tcgen05.mma.kind::f16 (M = 64, K = 16):  hi^T [hi | lo]  (N = 128) and
+//                        lo^T hi (N = 64, onto the second half) into one of four 128-column fp32 accumulators in TMEM;
+//                        tcgen05.commit frees the stage / hands the row over.  The large term hi^T hi has its own
+//                        64 columns: the accumulator is TRUNCATED on every MMA (measured: profiles/
+//                        r02_long_rows_tcgen05_v1_ab.txt), and adding the small terms into the same columns tripled
+//                        the number of truncations of the large sums;
 //   solvers (8 warps)    two groups of four: the four warps of a group drain four finished accumulators (a warp can read
-//                        only its own quarter of the TMEM lanes) into the packed panel layout of the blocked Cholesky,
+//                        only its own quarter of the TMEM lanes; large + small halves are added here) into the packed
+//                        panel layout of the blocked Cholesky,
 //                        then every warp adds sigma^2 (Y^T Y + lambda I), factors and solves one row in registers
 //                        (factor_solve of cholesky_device.cuh, shared with the mma.sync kernel) and stores x, also to
 //                        the peer replicas.
 // Rows are dealt to the CTAs round robin from the length-sorted work list, so all roles of a CTA walk the same
 // sequence without talking to each other; the only synchronisation is four sets of mbarriers (stage full / free,
-// accumulator done / free).  Deterministic: nothing depends on scheduling.
+// accumulator done / free).  Deterministic: nothing depends on scheduling.  Registers are rebalanced with setmaxnreg:
+// the solvers' warpgroups take 168 each, the producer / MMA warpgroups give back down to 80 (2 K registers of slack in the exchange).
 #include "cholesky_device.cuh"
 
 namespace als {
@@ -31,22 +36,27 @@ constexpr int kTcF = 64;
 constexpr int kTcStageNnz = 32;                     // nonzeros per ring stage
 constexpr int kTcTile = kTcStageNnz * 128;          // one fp16 tile: 32 rows of 64 halves
 constexpr int kTcStageBytes = 2 * kTcTile;          // hi | lo
-constexpr int kTcStages = 8;
-constexpr int kTcSlots = 8;                         // TMEM accumulators of 64 columns
-constexpr int kTcProducers = 3;
+constexpr int kTcStages = 12;
+constexpr int kTcSlots = 4;                         // TMEM accumulators of 128 columns: hi^T hi | hi^T lo + lo^T hi
+constexpr int kTcSlotCols = 128;
+constexpr int kTcProducers = 7;
 constexpr int kTcSolvers = 8;
 constexpr int kTcMmaWarp = kTcSolvers;
 constexpr int kTcThreads = 32 * (kTcSolvers + 1 + kTcProducers);
+static_assert(kTcThreads == 512, "four warpgroups: setmaxnreg below assumes 128 registers per thread at launch");
 constexpr int kTcSolverFloats = Cfg<4>::U_FLOATS + kTcF;  // packed panels + rhs
 constexpr int kTcOffRing = 0;
 constexpr int kTcOffSolver = kTcStages * kTcStageBytes;
 constexpr int kTcOffBpart = kTcOffSolver + kTcSolvers * kTcSolverFloats * 4;
 constexpr int kTcOffBar = kTcOffBpart + kTcSlots * kTcProducers * kTcF * 4;
-enum { kTcFull = 0, kTcEmpty = kTcStages, kTcRowDone = 2 * kTcStages, kTcSlotFree = 2 * kTcStages + kTcSlots,
-       kTcNumBars = 2 * kTcStages + 2 * kTcSlots };
+// "row done" has 2 kTcSlots barriers (row n uses n % 8): a solver group then sees consecutive phases of its own four
+// barriers.  With one barrier per accumulator the two groups would alternate on its phases, and a parity wait cannot
+// tell "two phases behind" from "done" (first attempt: deadlock, profiles/r02_long_rows_tcgen05_hang.txt).
+constexpr int kTcDone = 2 * kTcSlots;
+enum { kTcFull = 0, kTcEmpty = kTcStages, kTcRowDone = 2 * kTcStages, kTcSlotFree = 2 * kTcStages + kTcDone,
+       kTcNumBars = 2 * kTcStages + kTcDone + kTcSlots };
 constexpr int kTcSmem = kTcOffBar + 8 * kTcNumBars + 16 + 1024;
 static_assert(kTcSmem <= 227 * 1024, "shared memory budget");
-static_assert(kTcStages == 8 && kTcSlots == 8, "ring / slot arithmetic below uses & 7 and >> 3");
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) {
@@ -70,22 +80,23 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
 // MN-major fp16 operand tile, 128B swizzle: a row of the tile is one nonzero (K index) holding the 64 halves of the M / N
 // extent; groups of 8 nonzeros are 1024 bytes apart (SBO).  Descriptor version 1, layout type 2 = SWIZZLE_128B.
 #ifndef ALS_TC_LBO
-#define ALS_TC_LBO 1   // one 64-element atom along M / N: the leading offset is not used
-#define ALS_TC_SBO 64  // 1024 bytes between groups of 8 nonzeros
+#define ALS_TC_LBO 256  // 4096 bytes between the 64-element atoms along N: the hi tile, then the lo tile (N = 128 only)
+#define ALS_TC_SBO 64   // 1024 bytes between groups of 8 nonzeros
 #endif
 __device__ __forceinline__ uint64_t tc_desc_mn_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)ALS_TC_LBO << 16) | ((uint64_t)ALS_TC_SBO << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16: fp16 operands (format 0), fp32 accumulate, A and B MN-major (bits 15, 16), N = 64, M = 64
-constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// kind::f16: fp16 operands (format 0), fp32 accumulate, A and B MN-major (bits 15, 16), M = 64, N = 64 / 128
+constexpr uint32_t kTcIdesc64 = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+constexpr uint32_t kTcIdesc128 = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -106,6 +117,29 @@ __device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
+// Where the roles wait (cycles per warp), only in -DALS_TC_STATS builds (tools/long_stats.py)
+#ifdef ALS_TC_STATS
+__device__ unsigned long long g_tc_stats[160 * 16 * 4];
+__device__ volatile int *g_tc_dbg = nullptr;  // host-mapped: [8 CTAs][16 warps][4] = {what the warp waits on, row, stage, done flag}
+#define TC_TIMED(i, stmt)                \
+  do {                                   \
+    const long long t0__ = clock64();    \
+    stmt;                                \
+    wt[i] += clock64() - t0__;           \
+  } while (0)
+#define TC_MARK(code, a, b)                                                       \
+  do {                                                                            \
+    if (g_tc_dbg && blockIdx.x < 8 && (threadIdx.x & 31) == 0) {                  \
+      volatile int *d__ = g_tc_dbg + ((int)blockIdx.x * 16 + (threadIdx.x >> 5)) * 4; \
+      d__[0] = (code);                                                            \
+      d__[1] = (a);                                                               \
+      d__[2] = (b);                                                               \
+    }                                                                             \
+  } while (0)
+#else
+#define TC_TIMED(i, stmt) stmt
+#define TC_MARK(code, a, b)
+#endif
 __device__ __forceinline__ void tc_group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -132,16 +166,18 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
   };
   const float sigma = pow2_scale_below_2_14(sqrtf(__uint_as_float(*wmax_bits)) * __uint_as_float(*yabsmax_bits));
   const float sigma2 = sigma * sigma;
+#ifdef ALS_TC_STATS
+  long long wt[4] = {0, 0, 0, 0};
+  const long long t_start = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTcStages; ++i) {
       tc_mbar_init(bar(kTcFull + i), 1);
       tc_mbar_init(bar(kTcEmpty + i), 1);
     }
-    for (int i = 0; i < kTcSlots; ++i) {
-      tc_mbar_init(bar(kTcRowDone + i), 1 + kTcProducers);
-      tc_mbar_init(bar(kTcSlotFree + i), 4);
-    }
+    for (int i = 0; i < kTcDone; ++i) tc_mbar_init(bar(kTcRowDone + i), 1 + kTcProducers);
+    for (int i = 0; i < kTcSlots; ++i) tc_mbar_init(bar(kTcSlotFree + i), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kTcMmaWarp) {
@@ -155,6 +191,10 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  TC_MARK(1, 0, 0);
+  if (warp >= kTcSolvers) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  TC_MARK(2, 0, 0);  // both warpgroups of the producer / MMA side
   if (warp > kTcMmaWarp) {
     // ===== producers ==========================================================================================
     const int pw = warp - kTcMmaWarp - 1;
@@ -165,11 +205,11 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
       const WorkItem wi = load_item(n);
       const int nnz = (wi.slot == -1) ? wi.k1 - wi.k0 : 0;  // chunks of giant rows are not ours: an empty pass
       const int nst = (nnz + kTcStageNnz - 1) / kTcStageNnz;
-      const int slot = n & 7;
+      const int slot = n % kTcSlots;
       float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int s = 0; s < nst; ++s, ++G) {
         if (G % kTcProducers != pw) continue;
-        const int rs = G & 7, use = G >> 3;
+        const int rs = G % kTcStages, use = G / kTcStages;
         const int k = wi.k0 + kTcStageNnz * s + lane;
         const bool valid = k < wi.k1;
         const int idx = valid ? __ldg(indices + k) : -1;
@@ -179,20 +219,21 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
         const float sw = valid ? sigma * __fsqrt_rn(fmaxf(fabsf(c) - 1.f, 0.f)) : 0.f;
         const float cp = (valid && c > 0.f) ? c : 0.f;
         const int nvalid = min(kTcStageNnz, wi.k1 - (wi.k0 + kTcStageNnz * s));
-        const int nrow = nvalid > 16 ? 32 : 16;  // the MMA warp skips an empty second half as well
-        float4 v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int ir = __shfl_sync(0xffffffffu, idx, 2 * j + hl);
-          v[j] = (ir >= 0 && 2 * j < nrow) ? __ldg(Y4 + (int64_t)ir * (F / 4) + cl) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (use > 0) tc_mbar_wait(bar(kTcEmpty + rs), (uint32_t)((use - 1) & 1));  // the MMAs of the previous use are done
+        const int nhalf = nvalid > 16 ? 2 : 1;  // the MMA warp skips an empty second half as well
         unsigned char *hi = gbase + kTcOffRing + rs * kTcStageBytes, *lo = hi + kTcTile;
+        for (int h = 0; h < nhalf; ++h) {
+          float4 v[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int r = 2 * j + hl;
-          const float swr = __shfl_sync(0xffffffffu, sw, r), cpr = __shfl_sync(0xffffffffu, cp, r);
-          if (2 * j < nrow) {
+          for (int j = 0; j < 8; ++j) {
+            const int ir = __shfl_sync(0xffffffffu, idx, 16 * h + 2 * j + hl);
+            v[j] = (ir >= 0) ? __ldg(Y4 + (int64_t)ir * (F / 4) + cl) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          TC_MARK(11, n, G);
+          if (h == 0 && use > 0) TC_TIMED(0, tc_mbar_wait(bar(kTcEmpty + rs), (uint32_t)((use - 1) & 1)));  // the MMAs of the previous use are done
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = 16 * h + 2 * j + hl;
+            const float swr = __shfl_sync(0xffffffffu, sw, r), cpr = __shfl_sync(0xffffffffu, cp, r);
             bs.x = fmaf(cpr, v[j].x, bs.x);
             bs.y = fmaf(cpr, v[j].y, bs.y);
             bs.z = fmaf(cpr, v[j].z, bs.z);
@@ -214,12 +255,14 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
       bs.y += __shfl_xor_sync(0xffffffffu, bs.y, 16);
       bs.z += __shfl_xor_sync(0xffffffffu, bs.z, 16);
       bs.w += __shfl_xor_sync(0xffffffffu, bs.w, 16);
-      if (n >= kTcSlots) tc_mbar_wait(bar(kTcSlotFree + slot), (uint32_t)(((n >> 3) - 1) & 1));
+      TC_MARK(12, n, G);
+      if (n >= kTcSlots) TC_TIMED(1, tc_mbar_wait(bar(kTcSlotFree + slot), (uint32_t)((n / kTcSlots - 1) & 1)));
+      TC_MARK(13, n, G);
       if (lane < 16) *reinterpret_cast<float4 *>(bpart + (slot * kTcProducers + pw) * F + 4 * cl) = bs;
       __syncwarp();
-      if (lane == 0) tc_mbar_arrive(bar(kTcRowDone + slot));
+      if (lane == 0) tc_mbar_arrive(bar(kTcRowDone + n % kTcDone));
     }
-  } else if (warp == kTcMmaWarp) {
+  } else {
     // ===== MMA issue ==========================================================================================
     if (lane == 0) {
       int G = 0;
@@ -227,31 +270,36 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
         const WorkItem wi = load_item(n);
         const int nnz = (wi.slot == -1) ? wi.k1 - wi.k0 : 0;
         const int nst = (nnz + kTcStageNnz - 1) / kTcStageNnz;
-        const int slot = n & 7;
-        if (n >= kTcSlots) tc_mbar_wait(bar(kTcSlotFree + slot), (uint32_t)(((n >> 3) - 1) & 1));
+        const int slot = n % kTcSlots;
+        TC_MARK(21, n, G);
+        if (n >= kTcSlots) TC_TIMED(1, tc_mbar_wait(bar(kTcSlotFree + slot), (uint32_t)((n / kTcSlots - 1) & 1)));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(slot * F);
+        const uint32_t d = tmem_base + (uint32_t)(slot * kTcSlotCols);
         uint32_t acc = 0;
         for (int s = 0; s < nst; ++s, ++G) {
-          const int rs = G & 7;
-          tc_mbar_wait(bar(kTcFull + rs), (uint32_t)((G >> 3) & 1));
+          const int rs = G % kTcStages;
+          TC_MARK(22, n, G);
+          TC_TIMED(0, tc_mbar_wait(bar(kTcFull + rs), (uint32_t)((G / kTcStages) & 1)));
+          TC_MARK(23, n, G);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t hi = base + kTcOffRing + rs * kTcStageBytes, lo = hi + kTcTile;
           const int nk = (nnz - kTcStageNnz * s > 16) ? 2 : 1;
-          for (int ks = 0; ks < nk; ++ks) {  // small terms first
+          for (int ks = 0; ks < nk; ++ks) {
             const uint64_t dh = tc_desc_mn_sw128(hi + ks * 2048), dl = tc_desc_mn_sw128(lo + ks * 2048);
-            tc_mma(d, dl, dh, acc);
-            tc_mma(d, dh, dl, 1);
-            tc_mma(d, dh, dh, 1);
+            tc_mma(d, dh, dh, kTcIdesc128, acc);     // [hi^T hi | hi^T lo]: B spans the hi tile and, one LBO on, the lo tile
+            tc_mma(d + 64, dl, dh, kTcIdesc64, 1);   // + lo^T hi
             acc = 1;
           }
           tc_commit(bar(kTcEmpty + rs));
         }
-        tc_commit(bar(kTcRowDone + slot));
+        tc_commit(bar(kTcRowDone + n % kTcDone));
       }
     }
+  }
   } else {
     // ===== drain + solve ======================================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    TC_MARK(3, 0, 0);
     const int e = warp >> 2, q = warp & 3;
     const int g = lane >> 2, t = lane & 3;
     float *Uown = reinterpret_cast<float *>(gbase + kTcOffSolver) + warp * kTcSolverFloats;
@@ -261,10 +309,11 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
       for (int j = 0; j < 4; ++j) {
         const int n = 4 * B + j;
         if (n >= n_mine) break;
-        const int slot = n & 7;
+        const int slot = n % kTcSlots;
         const WorkItem wi = load_item(n);
         const bool real = wi.slot == -1 && wi.k1 > wi.k0;
-        tc_mbar_wait(bar(kTcRowDone + slot), (uint32_t)((n >> 3) & 1));
+        TC_MARK(32, n, j);
+        TC_TIMED(0, tc_mbar_wait(bar(kTcRowDone + n % kTcDone), (uint32_t)((n / kTcDone) & 1)));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (real) {
           float *Uj = reinterpret_cast<float *>(gbase + kTcOffSolver) + (4 * e + j) * kTcSolverFloats;
@@ -275,8 +324,11 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
           float *dst = Uj + po + (lane & 7) * ps - 8 * pm;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            float v[32];
-            tc_tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(slot * F + 32 * half), v);
+            float v[32], w[32];
+            tc_tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(slot * kTcSlotCols + 32 * half), v);
+            tc_tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(slot * kTcSlotCols + 64 + 32 * half), w);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] += w[c];  // large term + small terms
             if (lane < 16) {
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
@@ -301,7 +353,9 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
         __syncwarp();
         if (lane == 0) tc_mbar_arrive(bar(kTcSlotFree + slot));
       }
-      tc_group_sync(1 + e);  // the group's four matrices are complete in shared memory
+      TC_MARK(33, B, 0);
+      TC_TIMED(1, tc_group_sync(1 + e));  // the group's four matrices are complete in shared memory
+      TC_MARK(34, B, 0);
       const int n = 4 * B + q;
       if (n < n_mine) {
         const WorkItem wi = load_item(n);
@@ -338,15 +392,23 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
           __syncwarp();
           bool ok = true;
           float xx[(F + 31) / 32];
-          factor_solve<4>(st, Uown, zown, lane, ok, 0, xx);
+          TC_TIMED(2, factor_solve<4>(st, Uown, zown, lane, ok, 0, xx));
           if (ok) store_solution<F>(xx, X + xoff, lane, peers, n_peers, xoff);
           if (!ok && lane == 0) atomicMin(bad_row, (long long)(row_offset + wi.row));
           __syncwarp();
         }
       }
-      tc_group_sync(1 + e);  // the panel buffers are free for the next drain
+      TC_MARK(35, B, 0);
+      TC_TIMED(1, tc_group_sync(1 + e));  // the panel buffers are free for the next drain
     }
   }
+  TC_MARK(99, 0, 0);
+#ifdef ALS_TC_STATS
+  if (lane == 0 && blockIdx.x < 160) {
+    wt[3] = clock64() - t_start;
+    for (int i = 0; i < 4; ++i) g_tc_stats[((int)blockIdx.x * 16 + warp) * 4 + i] = (unsigned long long)wt[i];
+  }
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == kTcMmaWarp) {
@@ -356,6 +418,23 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
 }
 
 }  // namespace
+
+#ifdef ALS_TC_STATS
+extern "C" __attribute__((visibility("default"))) int als_debug_tc_stats(unsigned long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, g_tc_stats, sizeof(unsigned long long) * 160 * 16 * 4);
+}
+// progress markers in host-mapped memory: readable from the host while a kernel hangs
+extern "C" __attribute__((visibility("default"))) int als_debug_tc_hostbuf(int **host) {
+  int *h = nullptr, *d = nullptr;
+  cudaError_t e = cudaHostAlloc((void **)&h, 8 * 16 * 4 * sizeof(int), cudaHostAllocMapped);
+  if (e != cudaSuccess) return (int)e;
+  for (int i = 0; i < 8 * 16 * 4; ++i) h[i] = 0;
+  if ((e = cudaHostGetDevicePointer((void **)&d, h, 0)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpyToSymbol(g_tc_dbg, &d, sizeof(d))) != cudaSuccess) return (int)e;
+  *host = h;
+  return 0;
+}
+#endif
 
 bool cholesky_tc_eligible(const als_ctx *ctx, const als_csr *C, int ld) {
   return ld == kTcF && !ctx->knobs.long_legacy && C->neg_w_known && !C->has_neg_w;

@@ -43,6 +43,9 @@ for legacy in (int(a) for a in (sys.argv[1:] or ["1", "0"])):
     lng = deg[sample] > 48
     msg = (f"long_legacy={legacy} cholesky {ms:.3f} ms/iter | warm user half vs fp64: max {e.max():.2e} median {np.median(e):.2e} "
            f"(rows > 48: max {e[lng].max():.2e} median {np.median(e[lng]):.2e})")
+    d_s = deg[sample]
+    msg += " | median by nnz: " + ", ".join(
+        f"{lo}-{hi}: {np.median(e[(d_s > lo) & (d_s <= hi)]):.1e}" for lo, hi in ((48, 96), (96, 192), (192, 512), (512, 4096)) if ((d_s > lo) & (d_s <= hi)).any())
     if base is None:
         base = got
     else:
