@@ -301,7 +301,7 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   {
     struct { const char *env; const char *name; } table[] = {
         {"ALS_B200_SHORT_MAX", "short_max"}, {"ALS_B200_SHORT_SERIAL", "short_serial"}, {"ALS_B200_WHITEN_FMA", "whiten_fma"},
-        {"ALS_B200_GRAMIAN_MMA", "gramian_mma"}, {"ALS_B200_GRAMIAN_FMA", "gramian_fma"}, {"ALS_B200_TOPK_LEGACY", "topk_legacy"}, {"ALS_B200_LONG_LEGACY", "long_legacy"}, {"ALS_B200_CG_NV", "cg_nv"}};
+        {"ALS_B200_GRAMIAN_MMA", "gramian_mma"}, {"ALS_B200_GRAMIAN_FMA", "gramian_fma"}, {"ALS_B200_TOPK_LEGACY", "topk_legacy"}, {"ALS_B200_LONG_TC", "long_tc"}, {"ALS_B200_CG_NV", "cg_nv"}};
     for (const auto &t : table) {
       const char *e = getenv(t.env);
       if (!e) continue;
@@ -363,7 +363,7 @@ ALS_API int als_ctx_set_knob(als_ctx *ctx, const char *name, int value) {
   else if (!strcmp(name, "gramian_mma")) k.gramian_mma = value != 0;
   else if (!strcmp(name, "gramian_fma")) k.gramian_fma = value != 0;
   else if (!strcmp(name, "topk_legacy")) k.topk_legacy = value != 0;
-  else if (!strcmp(name, "long_legacy")) k.long_legacy = value != 0;
+  else if (!strcmp(name, "long_tc")) k.long_tc = value != 0;
   else if (!strcmp(name, "cg_nv")) {
     ALS_REQUIRE(value == 1 || value == 2 || value == 4, "als_ctx_set_knob: cg_nv must be 1, 2 or 4");
     k.cg_nv = value;

@@ -296,7 +296,7 @@ int run_cholesky(als_ctx *ctx, const als_csr *Cm, als_factors *X, const als_fact
     Cmut->wmax_valid = true;
     Cmut->neg_w_known = false;
   }
-  if (NB == 4 && !Cmut->neg_w_known && !ctx->knobs.long_legacy) {
+  if (NB == 4 && !Cmut->neg_w_known && ctx->knobs.long_tc) {
     // which long-row kernel: one 4-byte read-back per CSR (not per half), cached like the weight range
     unsigned flag = 0;
     ALS_CUDA(cudaMemcpyAsync(&flag, Cmut->wmax_dev + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));

@@ -59,7 +59,7 @@ struct als_knobs {
   int gramian_mma = 0;        // ALS_B200_GRAMIAN_MMA: legacy mma.sync Gramian
   int topk_legacy = 0;        // ALS_B200_TOPK_LEGACY: mma.sync top-k kernel for every call (no tcgen05 path)
   int gramian_fma = 0;        // ALS_B200_GRAMIAN_FMA: fp32 FMA Gramian instead of the tcgen05 one (64 padded factors)
-  int long_legacy = 0;        // ALS_B200_LONG_LEGACY: mma.sync kernel for the long rows of a Cholesky half (no tcgen05 path)
+  int long_tc = 0;            // ALS_B200_LONG_TC: experimental tcgen05 kernel for the long rows of a Cholesky half (cholesky_tc.cu)
   int cg_nv = 2;              // ALS_B200_CG_NV: float4 words per lane of the CG kernel (1 / 2 / 4)
 };
 

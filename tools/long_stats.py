@@ -8,6 +8,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 from implicit_b200 import _lib, synthetic
 ctx = _lib.Context(0)
+ctx.set_knob("long_tc", 1)
 Cui, X0, Y0, cfg = synthetic.config("C2", scale=float(os.environ.get("SC_SCALE", "1.0")))
 C = _lib.DeviceCSR.upload(ctx, Cui); T = C.transpose()
 X, Y = _lib.DeviceFactors.from_host(ctx, X0), _lib.DeviceFactors.from_host(ctx, Y0)
