@@ -48,8 +48,11 @@ class AlternatingLeastSquares:
             raise ValueError("implicit_b200 has no CPU implementation: use_gpu must be True")
         if np.dtype(dtype) != np.float32:
             raise ValueError("implicit_b200 computes in float32: dtype must be np.float32")
-        if factors > 128:
-            raise ValueError("implicit_b200 currently supports factors <= 128")
+        if factors > 1024:
+            raise ValueError("implicit_b200 supports factors <= 1024 (like the reference's CUDA solver, implicit/gpu/als.cu:177-178)")
+        if factors > 128 and not use_cg:
+            raise ValueError("factors > 128 need use_cg=True: the Cholesky solver covers factors <= 128 "
+                             "(the reference's GPU path is CG-only as well, implicit/gpu/als.py:126-165)")
         self.factors = factors
         self.regularization = regularization
         self.alpha = alpha

@@ -336,8 +336,8 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   }
   ALS_CUDA(cudaEventCreate(&ctx->ev0));
   ALS_CUDA(cudaEventCreate(&ctx->ev1));
-  ALS_CUDA(cudaMalloc(&ctx->G, sizeof(float) * 256 * 256));
-  ALS_CUDA(cudaMalloc(&ctx->Greg, sizeof(float) * 256 * 256));
+  ALS_CUDA(cudaMalloc(&ctx->G, sizeof(float) * (1024 * 1024 + 64)));     // up to 1024 padded factors + the failure flag slot
+  ALS_CUDA(cudaMalloc(&ctx->Greg, sizeof(float) * (1024 * 1024 + 64)));
   ALS_CUDA(cudaMalloc(&ctx->Pinv, sizeof(float) * 64 * 64));
   ALS_CUDA(cudaMalloc(&ctx->Ginv, sizeof(float) * 64 * 64));
   ALS_CUDA(cudaMalloc(&ctx->counters, sizeof(int32_t) * 16));
@@ -348,7 +348,7 @@ ALS_API int als_ctx_create(int device, als_ctx **out) {
   }
   ALS_CUDA(cudaMalloc(&ctx->status, sizeof(int32_t) * 4));
   ALS_CUDA(cudaMemset(ctx->status, 0, sizeof(int32_t) * 4));
-  ALS_CUDA(cudaMemset(ctx->G, 0, sizeof(float) * 256 * 256));
+  ALS_CUDA(cudaMemset(ctx->G, 0, sizeof(float) * (1024 * 1024 + 64)));
   ALS_CUDA(cudaMalloc(&ctx->dscalars, sizeof(double) * 8));
   *out = ctx;
   return ALS_OK;
@@ -688,14 +688,14 @@ ALS_API int als_csr_destroy(als_csr *csr) {
 ALS_API int als_factors_create(als_ctx *ctx, int64_t rows, int factors, als_factors **out) {
   ALS_REQUIRE(ctx && out, "als_factors_create: NULL argument");
   ALS_REQUIRE(rows >= 0 && factors > 0, "als_factors_create: bad shape (%lld, %d)", (long long)rows, factors);
-  ALS_REQUIRE(factors <= 256, "als_factors_create: factors=%d > 256 is not supported", factors);
+  ALS_REQUIRE(factors <= 1024, "als_factors_create: factors=%d > 1024 is not supported", factors);
   *out = nullptr;
   ALS_CUDA(cudaSetDevice(ctx->device));
   als_factors *f = new als_factors();
   f->ctx = ctx;
   f->rows = rows;
   f->f = factors;
-  f->ld = round_up(factors, 16);
+  f->ld = factors <= 128 ? round_up(factors, 16) : round_up(factors, 128);  // wide models: whole warps per factor row
   const int64_t bytes = sizeof(float) * std::max<int64_t>(rows, 1) * f->ld;
   // with a communicator the matrix will be exported over IPC (multi-GPU fit): take a cudaMalloc block right away
   f->pooled = ctx->world == 1;

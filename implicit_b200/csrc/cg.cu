@@ -29,7 +29,7 @@ struct CgCfg {
   static constexpr int LR = (V + NV - 1) / NV;       // lanes really needed per row
   static constexpr int L = LR <= 1 ? 1 : LR <= 2 ? 2 : LR <= 4 ? 4 : LR <= 8 ? 8 : LR <= 16 ? 16 : 32;  // lanes per group
   static constexpr int NG = 32 / L;                  // groups (nonzeros in flight) per warp
-  static_assert(F % 16 == 0 && F <= 128 && LR <= 32, "CG kernel handles padded factors <= 128");
+  static_assert(F % 16 == 0 && F <= 1024 && LR <= 32, "CG kernel: F / (4 NV) lanes per group must fit a warp");
 };
 
 template <int NV>
@@ -391,6 +391,22 @@ int launch_cg(als_ctx *ctx, const als_csr *C, als_factors *X, const als_factors 
   }
   // float4 words per lane (knob cg_nv): measured on B200: C2 (f=64) 6.0 ms/iter at 2 vs 6.6 (1) and 9.3 (4);
   // C3 (f=128) 9.9 vs 11.2 and 11.9
+  if (Y->ld > 128) {
+    // wide models (the reference's CUDA path takes up to 1024 factors, implicit/gpu/als.cu:177-178): the padded width is
+    // a multiple of 128, a whole warp per nonzero with ld / 128 float4 words per lane
+    switch (Y->ld % 128 == 0 ? Y->ld / 128 : 0) {
+      case 2: return run_cg<256, 2>(ctx, C, X, Y, cg_steps);
+      case 3: return run_cg<384, 3>(ctx, C, X, Y, cg_steps);
+      case 4: return run_cg<512, 4>(ctx, C, X, Y, cg_steps);
+      case 5: return run_cg<640, 5>(ctx, C, X, Y, cg_steps);
+      case 6: return run_cg<768, 6>(ctx, C, X, Y, cg_steps);
+      case 7: return run_cg<896, 7>(ctx, C, X, Y, cg_steps);
+      case 8: return run_cg<1024, 8>(ctx, C, X, Y, cg_steps);
+      default:
+        set_error("cg: factors padded to %d: beyond 128 the padded width must be a multiple of 128 up to 1024", Y->ld);
+        return ALS_E_UNSUPPORTED;
+    }
+  }
   const int nv = ctx->knobs.cg_nv;
 #define ALS_CG_CASE(FF)                                                   \
   case FF / 16:                                                           \

@@ -218,7 +218,7 @@ int launch_cholesky_wide(als_ctx *ctx, const als_csr *C, als_factors *X, const a
     case 7: return run_wide<7>(ctx, C, X, Y);
     case 8: return run_wide<8>(ctx, C, X, Y);
     default:
-      set_error("cholesky: factors=%d (padded %d) is not supported", Y->f, Y->ld);
+      set_error("cholesky: factors=%d (padded %d) is not supported: the Cholesky solver covers factors <= 128, wider models use CG", Y->f, Y->ld);
       return ALS_E_UNSUPPORTED;
   }
 }

@@ -190,6 +190,48 @@ __global__ void __launch_bounds__(256) gramian_partial_kernel(const float *__res
     for (int j = 0; j < T; ++j) out[(T * ty + i) * F + T * tx + j] = acc[i][j];
 }
 
+// 128 < padded factors <= 1024: one 64 x 64 tile of G per CTA and row chunk (blockIdx = (tile column, tile row, chunk)),
+// fp32 FMA register tiles of 4 x 4 per thread; the chunk partials are summed in fp64 in a fixed order like the others.
+__global__ void __launch_bounds__(256) gramian_wide_kernel(const float *__restrict__ Y, int64_t rows, int ld, float *__restrict__ partials,
+                                                           int64_t rows_per_part) {
+  __shared__ __align__(16) float A[16][64], B[16][64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int bj = blockIdx.x, bi = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.z * rows_per_part, r1 = min(rows, r0 + rows_per_part);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t r = r0; r < r1; r += 16) {
+    const int64_t row = r + ty;  // 16 rows x 16 float4 words: one word of each tile per thread
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+    if (row < r1) {
+      va = __ldg(reinterpret_cast<const float4 *>(Y + row * ld + 64 * bi) + tx);
+      vb = __ldg(reinterpret_cast<const float4 *>(Y + row * ld + 64 * bj) + tx);
+    }
+    reinterpret_cast<float4 *>(&A[ty][0])[tx] = va;
+    reinterpret_cast<float4 *>(&B[ty][0])[tx] = vb;
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const float4 a = *reinterpret_cast<const float4 *>(&A[rr][4 * ty]);
+      const float4 b = *reinterpret_cast<const float4 *>(&B[rr][4 * tx]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float *out = partials + (size_t)blockIdx.z * ld * ld;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4 *>(out + (size_t)(64 * bi + 4 * ty + i) * ld + 64 * bj + 4 * tx) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+
 // 32 consecutive elements x 8 groups of partials per block: group pg sums partials pg, pg + 8, ... in fp64, the 8
 // group sums are added in a fixed order -> deterministic, and the loads of a warp are contiguous.
 // (Multi-GPU) element n of G carries "a row of this rank's last solve was not positive definite": the all-reduce of
@@ -248,8 +290,32 @@ static int run_gramian_mma(als_ctx *ctx, const als_factors *Y, int grid) {
 int launch_gramian(als_ctx *ctx, const als_factors *Y) {
   const int F = Y->ld;
   if (F > 128) {
-    set_error("gramian: factors=%d (padded %d) > 128 is not supported yet", Y->f, F);
-    return ALS_E_UNSUPPORTED;
+    if (F % 128 != 0 || F > 1024) {
+      set_error("gramian: factors=%d (padded %d): beyond 128 the padded width must be a multiple of 128 up to 1024", Y->f, F);
+      return ALS_E_UNSUPPORTED;
+    }
+    const int T = F / 64;
+    const int64_t rows = std::max<int64_t>(Y->rows, 0);
+    int64_t np = std::min<int64_t>(ceil_div(std::max<int64_t>(rows, 1), 64), (int64_t)ctx->sm_count * 4 / (T * T) + 1);
+    const int nparts = (int)std::max<int64_t>(1, std::min<int64_t>(np, 64));
+    const int64_t rows_per_part = ceil_div(ceil_div(std::max<int64_t>(rows, 1), nparts), 16) * 16;
+    const int64_t need = (int64_t)nparts * F * F;
+    if (need > ctx->gram_partials_cap) {
+      if (ctx->gram_partials) {
+        ALS_CUDA(cudaStreamSynchronize(ctx->stream));
+        ALS_CUDA(cudaFree(ctx->gram_partials));
+        ctx->gram_partials = nullptr;
+      }
+      ALS_CUDA(cudaMalloc(&ctx->gram_partials, sizeof(float) * need));
+      ctx->gram_partials_cap = need;
+    }
+    ProfScope prof(ctx, kProfGramian);
+    gramian_wide_kernel<<<dim3(T, T, nparts), 256, 0, ctx->stream>>>(Y->d, rows, F, ctx->gram_partials, rows_per_part);
+    ALS_CUDA(cudaGetLastError());
+    gramian_reduce_kernel<<<(F * F + 31) / 32, 256, 0, ctx->stream>>>(ctx->gram_partials, nparts, F * F, ctx->G, ctx->bad_row);
+    ALS_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    return ALS_OK;
   }
   // The mma.sync version is ~25 % faster but the tensor core truncates its fp32 accumulator on every add, which
   // biases the all-positive diagonal of G by ~1e-6 relative; the FMA version (round to nearest) is the default.
@@ -268,7 +334,7 @@ int launch_gramian(als_ctx *ctx, const als_factors *Y) {
       ALS_CUDA(cudaFree(ctx->gram_partials));
       ctx->gram_partials = nullptr;
     }
-    const int64_t cap = (int64_t)ctx->sm_count * 2 * 128 * 128;
+    const int64_t cap = std::max<int64_t>(need, (int64_t)ctx->sm_count * 2 * 128 * 128);
     ALS_CUDA(cudaMalloc(&ctx->gram_partials, sizeof(float) * cap));
     ctx->gram_partials_cap = cap;
   }

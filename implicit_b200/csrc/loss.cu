@@ -97,6 +97,46 @@ __global__ void frob_trace_kernel(const float *__restrict__ A, const float *__re
   }
 }
 
+// 128 < padded factors <= 1024 (multiples of 128): one warp per row, NV float4 words per lane
+template <int NV>
+__global__ void __launch_bounds__(256)
+loss_nnz_wide_kernel(const int32_t *__restrict__ indices, const float *__restrict__ data, const float *__restrict__ Y,
+                     const float *__restrict__ X, int64_t row_offset, const WorkItem *__restrict__ work, int n_work,
+                     int32_t *counter, double *out) {
+  constexpr int F = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  double term = 0.0, conf_sum = 0.0;
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(counter, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n_work) break;
+    const int4 w = __ldg(reinterpret_cast<const int4 *>(work) + i);
+    if (w.w == -2) continue;
+    float4 x[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) x[q] = __ldg(reinterpret_cast<const float4 *>(X + (row_offset + w.x) * F) + lane + 32 * q);
+    for (int k = w.y; k < w.z; ++k) {
+      const int idx = __ldg(indices + k);
+      const float c = __ldg(data + k);
+      float d = 0.f;
+#pragma unroll
+      for (int q = 0; q < NV; ++q) d += dot4(__ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx * F) + lane + 32 * q), x[q]);
+      d = group_sum<32>(d);
+      const float conf = fabsf(c);
+      const float temp = (c > 0.f ? -2.f * c : 0.f) + (conf - 1.f) * d;
+      if (lane == 0) {
+        term += (double)(temp * d) + (double)conf;
+        conf_sum += (double)conf;
+      }
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(out + 0, term);
+    atomicAdd(out + 1, conf_sum);
+  }
+}
+
 __global__ void zero_loss_scalars(int32_t *counters, double *d) {
   if (threadIdx.x < 16) counters[threadIdx.x] = 0;
   if (threadIdx.x < 8) d[threadIdx.x] = 0.0;
@@ -115,6 +155,18 @@ int run_loss_nnz(als_ctx *ctx, const als_csr *C, const als_factors *X, const als
   return ALS_OK;
 }
 
+template <int NV>
+int run_loss_nnz_wide(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y) {
+  if (!C->n_work) return ALS_OK;
+  const int grid = (int)std::min<int64_t>(ceil_div(C->n_work, 8), (int64_t)ctx->sm_count * 8);
+  ProfScope prof(ctx, kProfLoss);
+  loss_nnz_wide_kernel<NV><<<grid, 256, 0, ctx->stream>>>(C->indices, C->data, Y->d, X->d, C->row_offset, C->work, (int)C->n_work,
+                                                          ctx->counters, ctx->dscalars);
+  ALS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return ALS_OK;
+}
+
 }  // namespace
 
 #define ALS_DISPATCH_F(ld, CALL)                                                              \
@@ -128,11 +180,23 @@ int run_loss_nnz(als_ctx *ctx, const als_csr *C, const als_factors *X, const als
     case 7: return CALL(112);                                                                 \
     case 8: return CALL(128);                                                                 \
     default:                                                                                  \
-      set_error("factors padded to %d > 128 are not supported yet", (ld));                    \
+      set_error("loss: factors padded to %d are not supported (<= 128 in steps of 16, <= 1024 in steps of 128)", (ld));                    \
       return ALS_E_UNSUPPORTED;                                                               \
   }
 
 static int loss_nnz_dispatch(als_ctx *ctx, const als_csr *C, const als_factors *X, const als_factors *Y) {
+  if (Y->ld > 128 && Y->ld % 128 == 0) {
+    switch (Y->ld / 128) {
+      case 2: return run_loss_nnz_wide<2>(ctx, C, X, Y);
+      case 3: return run_loss_nnz_wide<3>(ctx, C, X, Y);
+      case 4: return run_loss_nnz_wide<4>(ctx, C, X, Y);
+      case 5: return run_loss_nnz_wide<5>(ctx, C, X, Y);
+      case 6: return run_loss_nnz_wide<6>(ctx, C, X, Y);
+      case 7: return run_loss_nnz_wide<7>(ctx, C, X, Y);
+      case 8: return run_loss_nnz_wide<8>(ctx, C, X, Y);
+      default: break;
+    }
+  }
 #define CALL(FF) run_loss_nnz<FF>(ctx, C, X, Y)
   ALS_DISPATCH_F(Y->ld, CALL)
 #undef CALL

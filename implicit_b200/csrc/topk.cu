@@ -578,7 +578,8 @@ int launch_topk(als_ctx *ctx, const als_factors *items, const als_factors *queri
   a.scores = (float *)(base + o_sc);
 #define CALL(FF) run_topk_f<FF>(ctx, a)
   // k-lists of 2 * QB * k floats (QB = 16 rows per CTA beyond k = 64) must fit next to the operand tiles
-  const bool by_sort = !use_tc && k_eff > 64 && (int64_t)k_eff * 16 * 2 * 4 + 96 * 1024 > 227 * 1024;
+  // (also every model wider than 128 padded factors: its scores come from the generic one-CTA-per-query kernel)
+  const bool by_sort = !use_tc && ((k_eff > 64 && (int64_t)k_eff * 16 * 2 * 4 + 96 * 1024 > 227 * 1024) || items->ld > 128);
   if (by_sort) {
     return topk_by_sort(ctx, a, items->ld, ids_host, scores_host, k);
   }
