@@ -197,181 +197,181 @@ cholesky_tc_kernel(const int32_t *__restrict__ indices, const float *__restrict_
 
   TC_MARK(1, 0, 0);
   if (warp >= kTcSolvers) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-  TC_MARK(2, 0, 0);  // both warpgroups of the producer / MMA side
-  if (warp > kTcMmaWarp) {
-    // ===== producers ==========================================================================================
-    const int pw = warp - kTcMmaWarp - 1;
-    const int hl = lane >> 4, cl = lane & 15;  // the row of a pair, the 16-byte word of the factor row
-    unsigned char *rawb = gbase + kTcOffRaw + pw * kTcRawBytes;
-    // This warp's stages are the CTA's stages G = pw, pw + P, pw + 2 P, ...  A cursor names one of them: the row n
-    // (work item wi, nst stages), the stage s inside the row and G itself.
-    struct Cursor {
-      int n, s, nst, G;
-      WorkItem wi;
-    };
-    auto stages_of = [&](const WorkItem &w) -> int {
-      return (w.slot == -1) ? (w.k1 - w.k0 + kTcStageNnz - 1) / kTcStageNnz : 0;  // chunks of giant rows are not ours
-    };
-    auto settle = [&](Cursor &c) {  // move on to the row that holds stage c.s (counted from row c.n), or to the end
-      while (c.n < n_mine && c.s >= c.nst) {
-        c.s -= c.nst;
-        ++c.n;
-        if (c.n < n_mine) {
-          c.wi = load_item(c.n);
-          c.nst = stages_of(c.wi);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    TC_MARK(2, 0, 0);  // both warpgroups of the producer / MMA side
+    if (warp > kTcMmaWarp) {
+      // ===== producers ==========================================================================================
+      const int pw = warp - kTcMmaWarp - 1;
+      const int hl = lane >> 4, cl = lane & 15;  // the row of a pair, the 16-byte word of the factor row
+      unsigned char *rawb = gbase + kTcOffRaw + pw * kTcRawBytes;
+      // This warp's stages are the CTA's stages G = pw, pw + P, pw + 2 P, ...  A cursor names one of them: the row n
+      // (work item wi, nst stages), the stage s inside the row and G itself.
+      struct Cursor {
+        int n, s, nst, G;
+        WorkItem wi;
+      };
+      auto stages_of = [&](const WorkItem &w) -> int {
+        return (w.slot == -1) ? (w.k1 - w.k0 + kTcStageNnz - 1) / kTcStageNnz : 0;  // chunks of giant rows are not ours
+      };
+      auto settle = [&](Cursor &c) {  // move on to the row that holds stage c.s (counted from row c.n), or to the end
+        while (c.n < n_mine && c.s >= c.nst) {
+          c.s -= c.nst;
+          ++c.n;
+          if (c.n < n_mine) {
+            c.wi = load_item(c.n);
+            c.nst = stages_of(c.wi);
+          }
         }
-      }
-    };
-    // index / confidence of this lane's nonzero of the stage under the cursor
-    auto load_meta = [&](const Cursor &c, int &idx, float &cf) {
-      const int k = c.wi.k0 + kTcStageNnz * c.s + lane;
-      const bool valid = c.n < n_mine && k < c.wi.k1;
-      idx = valid ? __ldg(indices + k) : -1;
-      cf = valid ? __ldg(data + k) : 0.f;
-    };
-    // 16-byte cp.async gathers of half h (16 nonzeros) of a stage into this warp's landing zone; always one commit
-    auto issue_half = [&](int idx, int h, bool active) {
-      if (active) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ir = __shfl_sync(0xffffffffu, idx, 16 * h + 2 * j + hl);
-          if (ir >= 0)
-            cp_async16(reinterpret_cast<float *>(rawb + h * 4096 + (2 * j + hl) * 256 + cl * 16), Y + (int64_t)ir * F + 4 * cl);
-        }
-      }
-      cp_async_commit();
-    };
-    // finish row n for this producer: its share of b_u (zero when it had no stage in the row) and the hand-over
-    auto finish_row = [&](int n, float4 bs) {
-      const int slot = n % kTcSlots;
-      bs.x += __shfl_xor_sync(0xffffffffu, bs.x, 16);
-      bs.y += __shfl_xor_sync(0xffffffffu, bs.y, 16);
-      bs.z += __shfl_xor_sync(0xffffffffu, bs.z, 16);
-      bs.w += __shfl_xor_sync(0xffffffffu, bs.w, 16);
-      TC_MARK(12, n, 0);
-      if (n >= kTcSlots) TC_TIMED(1, tc_mbar_wait(bar(kTcSlotFree + slot), (uint32_t)((n / kTcSlots - 1) & 1)));
-      if (lane < 16) *reinterpret_cast<float4 *>(bpart + (slot * kTcProducers + pw) * F + 4 * cl) = bs;
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(bar(kTcRowDone + n % kTcDone));
-    };
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    Cursor cur;
-    cur.n = 0;
-    cur.s = pw;
-    cur.G = pw;
-    cur.nst = 0;
-    cur.wi = WorkItem{0, 0, 0, -1};
-    if (n_mine > 0) {
-      cur.wi = load_item(0);
-      cur.nst = stages_of(cur.wi);
-    }
-    settle(cur);
-    int idx;
-    float cf;
-    load_meta(cur, idx, cf);
-    int done_rows = 0;  // rows [0, done_rows) are finished
-    for (; done_rows < min(cur.n, n_mine); ++done_rows) finish_row(done_rows, zero4);
-    if (cur.n < n_mine) {
-      const int nv = min(kTcStageNnz, cur.wi.k1 - (cur.wi.k0 + kTcStageNnz * cur.s));
-      issue_half(idx, 0, true);
-      issue_half(idx, 1, nv > 16);
-    }
-    float4 bs = zero4;
-    while (cur.n < n_mine) {
-      // the stage after this one: its indices are fetched now, its gathers are issued as soon as a half of the landing zone is free
-      Cursor nxt = cur;
-      nxt.s += kTcProducers;
-      nxt.G += kTcProducers;
-      settle(nxt);
-      int nidx;
-      float ncf;
-      load_meta(nxt, nidx, ncf);
-      const int nnv = (nxt.n < n_mine) ? min(kTcStageNnz, nxt.wi.k1 - (nxt.wi.k0 + kTcStageNnz * nxt.s)) : 0;
-
-      const int rs = cur.G % kTcStages, use = cur.G / kTcStages;
-      const int nvalid = min(kTcStageNnz, cur.wi.k1 - (cur.wi.k0 + kTcStageNnz * cur.s));
-      // A += w y y^T with w = |c| - 1 (>= 0 here: CSRs with smaller weights take the mma.sync kernel);
-      // b += c y for c > 0   (_als.pyx:115-124)
-      const float sw = (idx >= 0) ? sigma * __fsqrt_rn(fmaxf(fabsf(cf) - 1.f, 0.f)) : 0.f;
-      const float cp = (idx >= 0 && cf > 0.f) ? cf : 0.f;
-      unsigned char *hi = gbase + kTcOffRing + rs * kTcStageBytes, *lo = hi + kTcTile;
-      TC_MARK(11, cur.n, cur.G);
-      if (use > 0) TC_TIMED(0, tc_mbar_wait(bar(kTcEmpty + rs), (uint32_t)((use - 1) & 1)));  // the MMAs of the previous use are done
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        cp_async_wait<1>();  // this half has landed (every lane reads back only what it copied itself)
-        if (h == 0 || nvalid > 16) {  // the MMA warp skips an empty second half as well
+      };
+      // index / confidence of this lane's nonzero of the stage under the cursor
+      auto load_meta = [&](const Cursor &c, int &idx, float &cf) {
+        const int k = c.wi.k0 + kTcStageNnz * c.s + lane;
+        const bool valid = c.n < n_mine && k < c.wi.k1;
+        idx = valid ? __ldg(indices + k) : -1;
+        cf = valid ? __ldg(data + k) : 0.f;
+      };
+      // 16-byte cp.async gathers of half h (16 nonzeros) of a stage into this warp's landing zone; always one commit
+      auto issue_half = [&](int idx, int h, bool active) {
+        if (active) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int r = 16 * h + 2 * j + hl;
-            const int ir = __shfl_sync(0xffffffffu, idx, r);
-            const float swr = __shfl_sync(0xffffffffu, sw, r), cpr = __shfl_sync(0xffffffffu, cp, r);
-            float4 v = *reinterpret_cast<const float4 *>(rawb + h * 4096 + (2 * j + hl) * 256 + cl * 16);
-            if (ir < 0) v = zero4;
-            bs.x = fmaf(cpr, v.x, bs.x);
-            bs.y = fmaf(cpr, v.y, bs.y);
-            bs.z = fmaf(cpr, v.z, bs.z);
-            bs.w = fmaf(cpr, v.w, bs.w);
-            uint32_t h0, l0, h1, l1;
-            split_f16_pair(swr * v.x, swr * v.y, h0, l0);
-            split_f16_pair(swr * v.z, swr * v.w, h1, l1);
-            const int off = r * 128 + (((cl >> 1) ^ (r & 7)) << 4) + (cl & 1) * 8;
-            *reinterpret_cast<uint2 *>(hi + off) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2 *>(lo + off) = make_uint2(l0, l1);
+            const int ir = __shfl_sync(0xffffffffu, idx, 16 * h + 2 * j + hl);
+            if (ir >= 0)
+              cp_async16(reinterpret_cast<float *>(rawb + h * 4096 + (2 * j + hl) * 256 + cl * 16), Y + (int64_t)ir * F + 4 * cl);
           }
         }
-        issue_half(nidx, h, nxt.n < n_mine && (h == 0 || nnv > 16));  // the landing zone of this half is free again
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> the tensor core's reads
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(bar(kTcFull + rs));
-      // rows that end between this stage and the next one of this warp
-      if (nxt.n != cur.n) {
-        finish_row(done_rows++, bs);
-        bs = zero4;
-        for (; done_rows < min(nxt.n, n_mine); ++done_rows) finish_row(done_rows, zero4);
-      }
-      cur = nxt;
-      idx = nidx;
-      cf = ncf;
-    }
-    cp_async_wait<0>();
-  } else {
-    // ===== MMA issue ==========================================================================================
-    if (lane == 0) {
-      int G = 0;
-      for (int n = 0; n < n_mine; ++n) {
-        const WorkItem wi = load_item(n);
-        const int nnz = (wi.slot == -1) ? wi.k1 - wi.k0 : 0;
-        const int nst = (nnz + kTcStageNnz - 1) / kTcStageNnz;
+        cp_async_commit();
+      };
+      // finish row n for this producer: its share of b_u (zero when it had no stage in the row) and the hand-over
+      auto finish_row = [&](int n, float4 bs) {
         const int slot = n % kTcSlots;
-        TC_MARK(21, n, G);
+        bs.x += __shfl_xor_sync(0xffffffffu, bs.x, 16);
+        bs.y += __shfl_xor_sync(0xffffffffu, bs.y, 16);
+        bs.z += __shfl_xor_sync(0xffffffffu, bs.z, 16);
+        bs.w += __shfl_xor_sync(0xffffffffu, bs.w, 16);
+        TC_MARK(12, n, 0);
         if (n >= kTcSlots) TC_TIMED(1, tc_mbar_wait(bar(kTcSlotFree + slot), (uint32_t)((n / kTcSlots - 1) & 1)));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(slot * kTcSlotCols);
-        uint32_t acc = 0;
-        for (int s = 0; s < nst; ++s, ++G) {
-          const int rs = G % kTcStages;
-          TC_MARK(22, n, G);
-          TC_TIMED(0, tc_mbar_wait(bar(kTcFull + rs), (uint32_t)((G / kTcStages) & 1)));
-          TC_MARK(23, n, G);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t hi = base + kTcOffRing + rs * kTcStageBytes, lo = hi + kTcTile;
-          const int nk = (nnz - kTcStageNnz * s > 16) ? 2 : 1;
-          for (int ks = 0; ks < nk; ++ks) {
-            const uint64_t dh = tc_desc_mn_sw128(hi + ks * 2048), dl = tc_desc_mn_sw128(lo + ks * 2048);
-            tc_mma(d, dh, dh, kTcIdesc128, acc);     // [hi^T hi | hi^T lo]: B spans the hi tile and, one LBO on, the lo tile
-            tc_mma(d + 64, dl, dh, kTcIdesc64, 1);   // + lo^T hi
-            acc = 1;
+        if (lane < 16) *reinterpret_cast<float4 *>(bpart + (slot * kTcProducers + pw) * F + 4 * cl) = bs;
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(bar(kTcRowDone + n % kTcDone));
+      };
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+      Cursor cur;
+      cur.n = 0;
+      cur.s = pw;
+      cur.G = pw;
+      cur.nst = 0;
+      cur.wi = WorkItem{0, 0, 0, -1};
+      if (n_mine > 0) {
+        cur.wi = load_item(0);
+        cur.nst = stages_of(cur.wi);
+      }
+      settle(cur);
+      int idx;
+      float cf;
+      load_meta(cur, idx, cf);
+      int done_rows = 0;  // rows [0, done_rows) are finished
+      for (; done_rows < min(cur.n, n_mine); ++done_rows) finish_row(done_rows, zero4);
+      if (cur.n < n_mine) {
+        const int nv = min(kTcStageNnz, cur.wi.k1 - (cur.wi.k0 + kTcStageNnz * cur.s));
+        issue_half(idx, 0, true);
+        issue_half(idx, 1, nv > 16);
+      }
+      float4 bs = zero4;
+      while (cur.n < n_mine) {
+        // the stage after this one: its indices are fetched now, its gathers are issued as soon as a half of the landing zone is free
+        Cursor nxt = cur;
+        nxt.s += kTcProducers;
+        nxt.G += kTcProducers;
+        settle(nxt);
+        int nidx;
+        float ncf;
+        load_meta(nxt, nidx, ncf);
+        const int nnv = (nxt.n < n_mine) ? min(kTcStageNnz, nxt.wi.k1 - (nxt.wi.k0 + kTcStageNnz * nxt.s)) : 0;
+
+        const int rs = cur.G % kTcStages, use = cur.G / kTcStages;
+        const int nvalid = min(kTcStageNnz, cur.wi.k1 - (cur.wi.k0 + kTcStageNnz * cur.s));
+        // A += w y y^T with w = |c| - 1 (>= 0 here: CSRs with smaller weights take the mma.sync kernel);
+        // b += c y for c > 0   (_als.pyx:115-124)
+        const float sw = (idx >= 0) ? sigma * __fsqrt_rn(fmaxf(fabsf(cf) - 1.f, 0.f)) : 0.f;
+        const float cp = (idx >= 0 && cf > 0.f) ? cf : 0.f;
+        unsigned char *hi = gbase + kTcOffRing + rs * kTcStageBytes, *lo = hi + kTcTile;
+        TC_MARK(11, cur.n, cur.G);
+        if (use > 0) TC_TIMED(0, tc_mbar_wait(bar(kTcEmpty + rs), (uint32_t)((use - 1) & 1)));  // the MMAs of the previous use are done
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          cp_async_wait<1>();  // this half has landed (every lane reads back only what it copied itself)
+          if (h == 0 || nvalid > 16) {  // the MMA warp skips an empty second half as well
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r = 16 * h + 2 * j + hl;
+              const int ir = __shfl_sync(0xffffffffu, idx, r);
+              const float swr = __shfl_sync(0xffffffffu, sw, r), cpr = __shfl_sync(0xffffffffu, cp, r);
+              float4 v = *reinterpret_cast<const float4 *>(rawb + h * 4096 + (2 * j + hl) * 256 + cl * 16);
+              if (ir < 0) v = zero4;
+              bs.x = fmaf(cpr, v.x, bs.x);
+              bs.y = fmaf(cpr, v.y, bs.y);
+              bs.z = fmaf(cpr, v.z, bs.z);
+              bs.w = fmaf(cpr, v.w, bs.w);
+              uint32_t h0, l0, h1, l1;
+              split_f16_pair(swr * v.x, swr * v.y, h0, l0);
+              split_f16_pair(swr * v.z, swr * v.w, h1, l1);
+              const int off = r * 128 + (((cl >> 1) ^ (r & 7)) << 4) + (cl & 1) * 8;
+              *reinterpret_cast<uint2 *>(hi + off) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2 *>(lo + off) = make_uint2(l0, l1);
+            }
           }
-          tc_commit(bar(kTcEmpty + rs));
+          issue_half(nidx, h, nxt.n < n_mine && (h == 0 || nnv > 16));  // the landing zone of this half is free again
         }
-        tc_commit(bar(kTcRowDone + n % kTcDone));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> the tensor core's reads
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(bar(kTcFull + rs));
+        // rows that end between this stage and the next one of this warp
+        if (nxt.n != cur.n) {
+          finish_row(done_rows++, bs);
+          bs = zero4;
+          for (; done_rows < min(nxt.n, n_mine); ++done_rows) finish_row(done_rows, zero4);
+        }
+        cur = nxt;
+        idx = nidx;
+        cf = ncf;
+      }
+      cp_async_wait<0>();
+    } else {
+      // ===== MMA issue ==========================================================================================
+      if (lane == 0) {
+        int G = 0;
+        for (int n = 0; n < n_mine; ++n) {
+          const WorkItem wi = load_item(n);
+          const int nnz = (wi.slot == -1) ? wi.k1 - wi.k0 : 0;
+          const int nst = (nnz + kTcStageNnz - 1) / kTcStageNnz;
+          const int slot = n % kTcSlots;
+          TC_MARK(21, n, G);
+          if (n >= kTcSlots) TC_TIMED(1, tc_mbar_wait(bar(kTcSlotFree + slot), (uint32_t)((n / kTcSlots - 1) & 1)));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d = tmem_base + (uint32_t)(slot * kTcSlotCols);
+          uint32_t acc = 0;
+          for (int s = 0; s < nst; ++s, ++G) {
+            const int rs = G % kTcStages;
+            TC_MARK(22, n, G);
+            TC_TIMED(0, tc_mbar_wait(bar(kTcFull + rs), (uint32_t)((G / kTcStages) & 1)));
+            TC_MARK(23, n, G);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t hi = base + kTcOffRing + rs * kTcStageBytes, lo = hi + kTcTile;
+            const int nk = (nnz - kTcStageNnz * s > 16) ? 2 : 1;
+            for (int ks = 0; ks < nk; ++ks) {
+              const uint64_t dh = tc_desc_mn_sw128(hi + ks * 2048), dl = tc_desc_mn_sw128(lo + ks * 2048);
+              tc_mma(d, dh, dh, kTcIdesc128, acc);     // [hi^T hi | hi^T lo]: B spans the hi tile and, one LBO on, the lo tile
+              tc_mma(d + 64, dl, dh, kTcIdesc64, 1);   // + lo^T hi
+              acc = 1;
+            }
+            tc_commit(bar(kTcEmpty + rs));
+          }
+          tc_commit(bar(kTcRowDone + n % kTcDone));
+        }
       }
     }
-  }
   } else {
     // ===== drain + solve ======================================================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");

@@ -27,6 +27,19 @@ def test_check_csr_warns_and_converts():
     assert not w
 
 
+def test_constructor_argument_checks():
+    """What the device library cannot do is refused at construction, like the reference refuses unknown devices
+    (implicit/als.py:60-85): no CPU path, float32 only, the Cholesky solver up to 128 factors, CG up to 1024."""
+    from implicit_b200 import AlternatingLeastSquares
+
+    for kw in (dict(use_gpu=False), dict(dtype=np.float64), dict(factors=129, use_cg=False), dict(factors=1025)):
+        with pytest.raises(ValueError):
+            AlternatingLeastSquares(**kw)
+    for kw in (dict(factors=128, use_cg=False), dict(factors=1024, use_cg=True), dict(factors=200)):
+        m = AlternatingLeastSquares(**kw)  # no device is touched before fit()
+        assert m.factors == kw["factors"]
+
+
 def test_check_random_state():
     a = check_random_state(42).random(3)
     b = check_random_state(42).random(3)
