@@ -20,7 +20,14 @@ for name, (A, U, V) in (("user half", (C, X, Y)), ("item half", (T, Y, X))):
     assert ctx.lib.als_debug_tc_stats(buf) == 0
     s = np.frombuffer(buf, dtype=np.uint64).reshape(160, 16, 4)[:148].astype(np.float64)
     tot = s[:, :, 3]
-    print(f"{name}: kernel cycles per CTA: mean {tot[:, 8].mean():.0f} max {tot[:, 8].max():.0f}")
+    t8 = tot[:, 8]
+    q = np.percentile(t8, [0, 10, 50, 90, 100])
+    print(f"{name}: kernel cycles per CTA: mean {t8.mean():.0f} max {t8.max():.0f}; percentiles 0/10/50/90/100: " + " ".join(f"{v:.0f}" for v in q))
+    order = np.argsort(t8)
+    print(f"  slowest CTAs (blockIdx): {order[-8:][::-1].tolist()}  fastest: {order[:8].tolist()}  corr(blockIdx, cycles) {np.corrcoef(np.arange(148), t8)[0, 1]:+.2f}")
+    slow = order[-15:]
+    print(f"  the 15 slowest CTAs: solvers in factor_solve {100 * (s[slow][:, :8, 2] / tot[slow][:, :8]).mean():.1f} %, waiting for rows {100 * (s[slow][:, :8, 0] / tot[slow][:, :8]).mean():.1f} %; "
+          f"producers waiting for accumulators {100 * (s[slow][:, 9:, 1] / tot[slow][:, 9:]).mean():.1f} %, for stages {100 * (s[slow][:, 9:, 0] / tot[slow][:, 9:]).mean():.1f} %")
     print(f"  solvers   : wait row_done {100 * (s[:, :8, 0] / tot[:, :8]).mean():.1f} %, group barriers {100 * (s[:, :8, 1] / tot[:, :8]).mean():.1f} %, "
           f"factor_solve {100 * (s[:, :8, 2] / tot[:, :8]).mean():.1f} %")
     print(f"  MMA warp  : wait stage full {100 * (s[:, 8, 0] / tot[:, 8]).mean():.1f} %, wait accumulator free {100 * (s[:, 8, 1] / tot[:, 8]).mean():.1f} %")
