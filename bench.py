@@ -83,16 +83,32 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe): `nvidia-smi -lms 100`, plus -- the
+    timed region of a multi-GPU step is shorter than nvidia-smi's start-up and sampling period -- an in-process NVML
+    poll every 10 ms (nvidia-ml-py; best effort: any failure leaves the nvidia-smi samples as the only source)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap", 0x4))
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.nvml_samples, self.nvml_stop, self.nvml_thread = None, [], threading.Event(), None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(self.index)))
+            self.nvml_thread = threading.Thread(target=self._poll, daemon=True)
+            self.nvml_thread.start()
+        except Exception:  # noqa: BLE001  (no NVML binding / no permission: nvidia-smi below is the recipe's source anyway)
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -102,19 +118,32 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        while not self.nvml_stop.is_set():
+            try:
+                self.nvml_samples.append((int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                          int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                                          int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+            except Exception:  # noqa: BLE001
+                return
+            time.sleep(0.010)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
+        self.nvml_stop.set()
+        if self.proc is None and not self.nvml_samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -129,8 +158,19 @@ class ClockSampler:
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+        n_smi = len(sm)
+        try:
+            nv = self.nvml[0] if self.nvml else None
+            for c, m, bits in list(self.nvml_samples):
+                sm.append(float(c))
+                mx.append(float(m))
+                for name, attr, default in self.NVML_REASONS:
+                    if bits & int(getattr(nv, attr, default)):
+                        reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_nvidia_smi": n_smi, "reasons": sorted(reasons)}
 
 
 def pinned_csr(Cui):
