@@ -75,6 +75,27 @@ def test_port_matches_compiled_reference(use_cg):
     assert PORT.calculate_loss(Cui, Xa, Yw, 0.01) == pytest.approx(ref.calculate_loss(Cui, Xa, Yw, 0.01), rel=1e-6)
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built in this checkout")
+def test_port_matches_compiled_reference_on_a_wide_model():
+    """192 factors (the widths of tests/test_gpu_wide.py): the checker itself must not care about the width."""
+    from implicit_b200 import synthetic
+
+    ref = oracle.get("ref")
+    Cui = synthetic.power_law_csr(200, 150, 3000, 78, negative_fraction=0.05)
+    rng = np.random.default_rng(5)
+    X = (rng.standard_normal((200, 192)) * 0.1).astype(np.float32)
+    Y = (rng.standard_normal((150, 192)) * 0.1).astype(np.float32)
+    Xa, Xb = X.copy(), X.copy()
+    ref.least_squares_cg(Cui, Xa, Y, 0.01, cg_steps=3)
+    PORT.least_squares_cg(Cui, Xb, Y, 0.01, cg_steps=3)
+    assert row_err(Xb, Xa).max() < 1e-5
+    assert PORT.calculate_loss(Cui, Xa, Y, 0.01) == pytest.approx(ref.calculate_loss(Cui, Xa, Y, 0.01), rel=1e-6)
+    ia, sa = ref.topk(Y, Xa[:20], 7, filter_query_items=Cui[:20])
+    ib, sb = PORT.topk(Y, Xa[:20], 7, filter_query_items=Cui[:20])
+    np.testing.assert_allclose(sb, sa, rtol=1e-5, atol=1e-7)
+    assert (ia == ib).mean() > 0.98
+
+
 # ---- the reference's own known-answer tests for this path ------------------------------------------
 @pytest.mark.parametrize("use_cg", [False, True])
 def test_factorize(use_cg):
