@@ -63,3 +63,37 @@ def test_graft_entry_build_runs():
 
     if os.path.isdir("/root/reference"):
         assert oracle.have_ref() and oracle.have_ref_evaluation()
+
+
+def test_library_holds_the_blackwell_paths():
+    """The sm_100a-specific data paths are in the built library, kernel by kernel (cuobjdump, no GPU needed): tcgen05
+    MMAs with TMEM loads and TMA in the dense pre-pass, the Gramian and the top-k kernel; tcgen05 + setmaxnreg in the
+    opt-in long-row kernel.  A refactor that silently falls back to mma.sync everywhere fails here."""
+    import shutil
+    import subprocess
+
+    from implicit_b200 import _build
+
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _build.build()], capture_output=True, text=True).stdout
+    per_kernel = {}
+    fn = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            per_kernel[fn] = set()
+        elif fn is not None:
+            for m in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "USETMAXREG"):
+                if m in line:
+                    per_kernel[fn].add(m)
+
+    def has(kernel, *mnemonics):
+        hits = [ms for name, ms in per_kernel.items() if kernel in name]
+        return bool(hits) and all(any(m in ms for ms in hits) for m in mnemonics)
+
+    assert has("dense_apply_kernel", "UTCHMMA", "UTMALDG", "UTMASTG", "LDTM")
+    assert has("gramian_tc_kernel", "UTCHMMA", "UTMALDG", "LDTM")
+    assert has("topk_tc_kernel", "UTCHMMA", "UTMALDG", "LDTM")
+    assert has("cholesky_tc_kernel", "UTCHMMA", "LDTM", "USETMAXREG")
